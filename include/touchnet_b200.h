@@ -1,0 +1,146 @@
+/* touchnet_b200 — C ABI of the B200-native TouchNet hot path.
+ *
+ * This header is the drop-in boundary: every entry point replaces one third-party kernel call site that the
+ * reference (xingchensong/TouchNet) reaches from Python.  "Reference interface" below names the reference
+ * file:line the call replaces (paths relative to the TouchNet checkout; `hf:` = transformers 4.51.3,
+ * `ta:` = torchaudio).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch caching allocator); kernels never allocate
+ *     and never synchronise; work is enqueued on `stream` (a cudaStream_t / CUstream; NULL = legacy default).
+ *   - bf16 tensors are row-major with explicit leading dimensions (in elements).
+ *   - return value 0 = success; non-zero = error, message via tn_last_error() (thread-local).
+ *   - entry points are re-entrant and stream-ordered (FSDP2 side streams, activation-checkpoint recompute and the
+ *     autograd device thread may all call concurrently on different streams).
+ */
+#ifndef TOUCHNET_B200_H
+#define TOUCHNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOUCHNET_B200_VERSION 100
+
+typedef void* tn_stream_t; /* cudaStream_t */
+
+const char* tn_last_error(void);
+int tn_version(void);
+/* 0 iff the current CUDA device is compute capability 10.x (B200). */
+int tn_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * GEMM  D[M,N] = A·Bᵀ (+ R)          tcgen05 / TMEM / TMA, bf16 in, fp32 accumulate.
+ *   a_mn = 0: A stored [M,K] (K contiguous, lda)      a_mn = 1: A stored [K,M] (M contiguous, lda)
+ *   b_mn = 0: B stored [N,K] (K contiguous, ldb)      b_mn = 1: B stored [K,N] (N contiguous, ldb)
+ *   d_f32 = 0: D (and R) bf16;  d_f32 = 1: D (and R) fp32.  R optional (NULL), may alias D (accumulate).
+ *   forward  y = x·Wᵀ      : a_mn=0, b_mn=0   (F.linear; hf:models/llama/modeling_llama.py:251-289 q/k/v/o_proj,
+ *                                               :182-184 down_proj; touchnet/models/touch_audio/modeling_touch_audio.py:127 projector)
+ *   dgrad    dx = dy·W     : a_mn=0, b_mn=1
+ *   wgrad    dW = dyᵀ·x    : a_mn=1, b_mn=1
+ */
+int tn_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
+                 int d_f32, const void* R, int64_t ldr, int M, int N, int K, tn_stream_t stream);
+
+/* Fused gate/up projection + SwiGLU:  G = X·Wgᵀ, U = X·Wuᵀ, H = silu(G)⊙U   (all bf16, [M,N]; X [M,K]; Wg,Wu [N,K]).
+ * G and U may be NULL (inference: only H is written).
+ * Reference interface: hf:models/llama/modeling_llama.py:182-184 LlamaMLP.forward (gate_proj, up_proj, act_fn, mul). */
+int tn_gemm_swiglu_bf16(const void* X, int64_t ldx, const void* Wg, const void* Wu, int64_t ldw, void* G, void* U,
+                        void* H, int64_t ldh, int M, int N, int K, tn_stream_t stream);
+
+/* SwiGLU backward (elementwise): dG = dH⊙U⊙silu'(G), dU = dH⊙silu(G).  bf16 [M,N] contiguous rows (ld). */
+int tn_swiglu_bwd_bf16(const void* G, const void* U, const void* dH, void* dG, void* dU, int64_t rows, int64_t cols,
+                       int64_t ld, tn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * RMSNorm (+ fused residual add).   hf:models/llama/modeling_llama.py:62-67 LlamaRMSNorm.forward and the residual
+ * adds of LlamaDecoderLayer.forward :303-333.
+ *   fwd: if R != NULL: S = X + R (bf16, written to S_out if non-NULL) else S = X;
+ *        Y = w ⊙ bf16(S · rsqrt(mean(S²)+eps));  rstd[row] (fp32) saved for backward.
+ *   bwd: dS = rstd·(w⊙dY) − rstd³/d · S · Σ(w⊙dY⊙S)  (+ dS_extra if non-NULL: gradient flowing through the residual
+ *        branch), dW_partial[blk, d] fp32 partial sums (caller reduces over blk; num_partials returned rows).
+ */
+int tn_rmsnorm_fwd_bf16(const void* X, const void* R, const void* w, int w_is_f32, void* S_out, void* Y, float* rstd,
+                        int64_t rows, int d, float eps, tn_stream_t stream);
+int tn_rmsnorm_bwd_bf16(const void* S, const void* dY, const void* dS_extra, const void* w, int w_is_f32,
+                        const float* rstd, void* dS, float* dW_partial, int num_partials, int64_t rows, int d,
+                        tn_stream_t stream);
+int tn_rmsnorm_bwd_num_partials(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * RoPE.  hf:models/llama/modeling_llama.py:124-168 (LlamaRotaryEmbedding.forward + apply_rotary_pos_emb), called at
+ * touchnet/models/llama/pipeline_llama.py:83.  position_ids restart per packed document
+ * (touchnet/models/llama/processing_llama.py:98).
+ *   tn_rope_table: cos/sin[b*T+t, j] = bf16(cos/sin(position_ids[b,t] · inv_freq[j]) · attention_scaling), j < hd/2
+ *   tn_rope_apply: in-place x ← x·cos + rotate_half(x)·sin on X [rows, n_heads, hd] (row stride ldx elements);
+ *                  inverse != 0 applies the transpose rotation (backward).
+ */
+int tn_rope_table(const int64_t* position_ids, const float* inv_freq, float attention_scaling, void* cos_out,
+                  void* sin_out, int64_t rows, int half_dim, tn_stream_t stream);
+int tn_rope_apply_bf16(void* X, int64_t ldx, const void* cos_tab, const void* sin_tab, int64_t rows, int n_heads,
+                       int head_dim, int inverse, tn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Packed-sequence (block-causal "document") attention, head_dim = 128, bf16, GQA.
+ * Reference interface: hf:integrations/flex_attention.py:136-247 make_flex_block_causal_mask + :262-364
+ * flex_attention_forward (selected by "attn_implementation": "flex_attention",
+ * examples/text/pretrain/fineweb-edu/config/Llama-3_2-1B.json:7; checked at touchnet/bin/train.py:129-131).
+ *   mask: allow[b,q,k] = (q >= k) && doc[b,q] == doc[b,k] && doc[b,q] > 0      (doc = attention_mask ids, int32)
+ *   Q [B,T,H,128], K/V [B,T,KV,128], O [B,T,H,128] with strides (elements): token stride ld*, batch stride = T*ld*.
+ *   lse [B,H,T] fp32 (natural log; +inf for fully-masked rows whose O is exactly 0).
+ *   tn_attn_prep builds the per-(b, q-block) kv ranges (device side, no host sync); meta: int32 [B, ceil(T/128), 4].
+ */
+int tn_attn_prep(const int32_t* doc_ids, int32_t* meta, int B, int T, tn_stream_t stream);
+int tn_attn_fwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                     int64_t ldo, float* lse, const int32_t* doc_ids, const int32_t* meta, int B, int T, int H, int KV,
+                     float scale, tn_stream_t stream);
+/* backward: delta [B,H,T] fp32 workspace; dQ [B,T,H,128], dK/dV [B,T,KV,128] bf16. */
+int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, const void* O,
+                     int64_t ldo, const void* dO, int64_t lddo, const float* lse, float* delta, void* dQ, int64_t lddq,
+                     void* dK, int64_t lddk, void* dV, int64_t lddv, const int32_t* doc_ids, const int32_t* meta, int B,
+                     int T, int H, int KV, float scale, tn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Audio frontend.
+ *   tn_fbank: touchnet/data/functions.py:117-134 audio_compute_fbank → ta:compliance/kaldi.py:514-645 (snip_edges,
+ *     remove DC, pre-emphasis, povey window, |rfft|², HTK mel bank, log) batched over utterances packed back to back.
+ *     wav: fp32 in [-1,1] (wav_is_i16 = 0; scaled by 2^15 like functions.py:125) or int16 PCM (wav_is_i16 = 1).
+ *     utt_offsets[n_utts+1]: sample offsets; frame_offsets[n_utts+1]: output row offsets (m_i = 1+(N_i-win)/shift).
+ *     window [frame_len] and mel_filters [n_mels, n_fft/2+1] are supplied by the host mirror (povey window and HTK
+ *     mel bank computed exactly as ta:compliance/kaldi.py:90-103 and :436-511 do).
+ *   tn_logmel: touchnet/data/functions.py:159-190 audio_compute_log_mel_spectrogram (whisper-style: hann STFT,
+ *     center/reflect, power, Slaney mel (caller supplies filters [n_mels, n_fft/2+1] fp32), log10, per-utterance
+ *     max-8 clamp, (x+4)/4).  Two passes: tn_logmel_power writes log10 mel + per-utterance max (atomic), then
+ *     tn_logmel_finish applies the clamp/affine in place.
+ *   tn_feat_stack: touchnet/data/functions.py:258-286 audiofeat_stack (left/right replicate padding, stack/stride,
+ *     optional per-row mean / unbiased-std normalisation).
+ */
+int tn_fbank_f32(const void* wav, int wav_is_i16, const int64_t* utt_offsets, const int64_t* frame_offsets, int n_utts,
+                 int64_t total_frames, int frame_len, int frame_shift, int n_fft, const float* window,
+                 const float* mel_filters, int n_mels, float preemph, float* out, tn_stream_t stream);
+int tn_logmel_power_f32(const float* wav, const int64_t* utt_offsets, const int64_t* frame_offsets, int n_utts,
+                        int64_t total_frames, int n_fft, int hop, const float* window, const float* mel_filters,
+                        int n_mels, float* out, float* utt_max, tn_stream_t stream);
+int tn_logmel_finish_f32(float* feats, const int64_t* frame_offsets, const float* utt_max, int n_utts,
+                         int64_t total_frames, int n_mels, tn_stream_t stream);
+int tn_feat_stack_f32(const float* feats, const int64_t* frame_offsets, const int64_t* out_offsets, int n_utts,
+                      int64_t total_out_rows, int n_mels, int stack, int stride, int normalize, float* out,
+                      tn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Small fused elementwise helpers on the path.
+ *   tn_embed_add: E = embed[input_ids] + P   (touchnet/models/touch_audio/modeling_touch_audio.py:124-131), with the
+ *     NaN check of :133-134 folded in (nan_flag[0] set to 1 if any NaN; read lazily by the caller, no sync here).
+ *   tn_cast_f32_bf16: fp32 master → bf16 working copy (what FSDP2 MixedPrecisionPolicy does at all-gather,
+ *     touchnet/models/helper_func.py:163).
+ */
+int tn_embed_add_bf16(const int64_t* input_ids, const void* embed, int embed_is_f32, const void* P, void* E,
+                      int32_t* nan_flag, int64_t rows, int d, int64_t vocab, tn_stream_t stream);
+int tn_cast_f32_bf16(const float* src, void* dst, int64_t n, tn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOUCHNET_B200_H */

@@ -1,0 +1,422 @@
+// touchnet_b200 :: packed-sequence ("document") causal attention, backward.  head_dim 128, bf16, GQA.
+//
+// Backward of the FlexAttention call the reference reaches through hf:integrations/flex_attention.py:262-364
+// (autograd of torch.nn.attention.flex_attention with the block-causal document mask of :136-247).
+//
+// Three launches, no atomics, deterministic:
+//   attn_delta_kernel            delta[b,h,t] = Σ_d O·dO
+//   attn_bwd_kernel<true>        one CTA per (kv block, kv head): loops over the q heads of the GQA group and the
+//                                q blocks that attend to it;  Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ (TMEM), Pᵀ/dSᵀ -> smem,
+//                                dV += Pᵀ·dO, dK += dSᵀ·Q accumulate in TMEM across the whole loop.
+//   attn_bwd_kernel<false>       one CTA per (q block, head): S = Q·Kᵀ, dP = dO·Vᵀ, dS -> smem, dQ += dS·K.
+// Both use the same skeleton: two resident 128-row tiles, two streamed 64-row tiles (2-stage TMA ring), double
+// buffered score tiles in TMEM, one softmax warpgroup (thread = resident row), one MMA-issuing thread.
+#include "../../include/touchnet_b200.h"
+#include "attn_common.cuh"
+#include "host.h"
+
+namespace tn {
+
+constexpr int BWD_THREADS = 192;
+constexpr int SUB = 64;                               // streamed rows per iteration
+constexpr int RES_BYTES = ATT_BLK * ATT_HD * 2;       // 32 KB resident tile (2 chunks of 16 KB)
+constexpr int RES_CHUNK = RES_BYTES / 2;
+constexpr int STR_BYTES = SUB * ATT_HD * 2;           // 16 KB streamed tile (2 chunks of 8 KB)
+constexpr int STR_CHUNK = STR_BYTES / 2;
+constexpr int PT_BYTES = ATT_BLK * SUB * 2;           // 16 KB  [128 rows x 128 B]
+
+struct BwdSmem {
+  static constexpr int R1 = 0;
+  static constexpr int R2 = R1 + RES_BYTES;
+  static constexpr int T = R2 + RES_BYTES;                  // 2 stages x (T1, T2)
+  static constexpr int PT = T + 2 * 2 * STR_BYTES;
+  static constexpr int DST = PT + PT_BYTES;
+  static constexpr int COL = DST + PT_BYTES;                // 2 x {lse2[64], delta[64], doc[64]}
+  static constexpr int BARS = COL + 2 * 3 * SUB * 4;
+  static constexpr int TOTAL = BARS + 256;
+  static constexpr int ALLOC = TOTAL + 1024;
+};
+
+struct AttnBwdParams {
+  const int32_t* doc;
+  const AttnMeta* meta;
+  const float* lse;
+  const float* delta;
+  bf16* out1;   // dKdV: dV ; dQ: dQ      (all-masked fast path)
+  bf16* out2;   // dKdV: dK
+  int64_t ld1, ld2;
+  int B, T, H, KV, nblk;
+  float scale, scale_log2;
+};
+
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ O, int64_t ldo,
+                                                         const bf16* __restrict__ dO, int64_t lddo,
+                                                         float* __restrict__ delta, int B, int T, int H) {
+  // half-warp per (b, t, h): 16 lanes x 8 elements
+  const int64_t pair = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 4;
+  const int sub = threadIdx.x & 15;
+  const int64_t total = int64_t(B) * T * H;
+  float acc = 0.f;
+  if (pair < total) {
+    const int h = int(pair % H);
+    const int64_t bt = pair / H;
+    const uint4 a = *reinterpret_cast<const uint4*>(O + bt * ldo + int64_t(h) * ATT_HD + sub * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(dO + bt * lddo + int64_t(h) * ATT_HD + sub * 8);
+    acc = bf16lo(a.x) * bf16lo(g.x) + bf16hi(a.x) * bf16hi(g.x) + bf16lo(a.y) * bf16lo(g.y) + bf16hi(a.y) * bf16hi(g.y) +
+          bf16lo(a.z) * bf16lo(g.z) + bf16hi(a.z) * bf16hi(g.z) + bf16lo(a.w) * bf16lo(g.w) + bf16hi(a.w) * bf16hi(g.w);
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (pair < total && sub == 0) {
+    const int h = int(pair % H);
+    const int64_t bt = pair / H;
+    const int64_t b = bt / T, t = bt - b * T;
+    delta[(b * H + h) * T + t] = acc;
+  }
+}
+
+// DKDV = true : resident (R1,R2) = (K,V) block `blk` of kv head `hy`; streamed (T1,T2) = (Q,dO) 64-row sub-blocks
+// DKDV = false: resident (R1,R2) = (Q,dO) block `blk` of head `hy`;   streamed (T1,T2) = (K,V) 64-row sub-blocks
+template <bool DKDV>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
+                const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2,
+                const __grid_constant__ CUtensorMap tmOut1, const __grid_constant__ CUtensorMap tmOut2,
+                const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sR1 = smem + BwdSmem::R1;
+  uint8_t* sR2 = smem + BwdSmem::R2;
+  uint8_t* sT = smem + BwdSmem::T;
+  uint8_t* sPT = smem + BwdSmem::PT;
+  uint8_t* sDST = smem + BwdSmem::DST;
+  float* sCol = reinterpret_cast<float*>(smem + BwdSmem::COL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BARS);
+  uint64_t* r_full = bars + 0;
+  uint64_t* t_full = bars + 1;    // [2]
+  uint64_t* t_empty = bars + 3;   // [2]
+  uint64_t* xy_full = bars + 5;   // [2]
+  uint64_t* pds_full = bars + 7;
+  uint64_t* acc_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const int blk = DKDV ? int(blockIdx.x) : p.nblk - 1 - int(blockIdx.x);
+  const int hy = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / p.KV;
+  const int r0 = blk * ATT_BLK;  // first resident row (token position)
+  const AttnMeta meta = p.meta[b * p.nblk + blk];
+  // streamed block range and iteration count
+  const int sb_lo = DKDV ? blk : meta.kv_lo;
+  const int sb_end = DKDV ? meta.q_end : meta.kv_end;
+  const int nsb = sb_end > sb_lo ? sb_end - sb_lo : 0;
+  const int n = (DKDV ? G : 1) * nsb * 2;
+
+  if (n == 0) {
+    // no (query, key) pair touches this block: gradients are exactly zero
+    for (int i = threadIdx.x; i < ATT_BLK * (ATT_HD / 8); i += BWD_THREADS) {
+      const int r = i / (ATT_HD / 8), c = i % (ATT_HD / 8);
+      if (r0 + r < p.T) {
+        const int64_t tok = int64_t(b) * p.T + r0 + r;
+        *reinterpret_cast<uint4*>(p.out1 + tok * p.ld1 + int64_t(hy) * ATT_HD + c * 8) = make_uint4(0, 0, 0, 0);
+        if (DKDV) *reinterpret_cast<uint4*>(p.out2 + tok * p.ld2 + int64_t(hy) * ATT_HD + c * 8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    return;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmR1); tma_prefetch_desc(&tmR2); tma_prefetch_desc(&tmT1); tma_prefetch_desc(&tmT2);
+    tma_prefetch_desc(&tmOut1);
+    if (DKDV) tma_prefetch_desc(&tmOut2);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(r_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 1); mbar_init(&xy_full[s], 1);
+    }
+    mbar_init(pds_full, 128);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc1 = tmem_base + 256, tmem_acc2 = tmem_base + 384;
+
+  // iteration t -> (streamed head, streamed row0)
+  auto iter_head = [&](int t) { return DKDV ? hy * G + t / (nsb * 2) : hy / G; };
+  auto iter_row0 = [&](int t) { const int u = DKDV ? t % (nsb * 2) : t; return (sb_lo + (u >> 1)) * ATT_BLK + (u & 1) * SUB; };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(r_full, 2 * RES_BYTES);
+      tma_load_3d(sR1, &tmR1, r_full, hy * ATT_HD, r0, b);
+      tma_load_3d(sR1 + RES_CHUNK, &tmR1, r_full, hy * ATT_HD + 64, r0, b);
+      tma_load_3d(sR2, &tmR2, r_full, hy * ATT_HD, r0, b);
+      tma_load_3d(sR2 + RES_CHUNK, &tmR2, r_full, hy * ATT_HD + 64, r0, b);
+      for (int t = 0; t < n; ++t) {
+        const int s = t & 1;
+        mbar_wait(&t_empty[s], ((t >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&t_full[s], 2 * STR_BYTES);
+        uint8_t* d1 = sT + s * 2 * STR_BYTES;
+        uint8_t* d2 = d1 + STR_BYTES;
+        const int hs = iter_head(t), row0 = iter_row0(t);
+        tma_load_3d(d1, &tmT1, &t_full[s], hs * ATT_HD, row0, b);
+        tma_load_3d(d1 + STR_CHUNK, &tmT1, &t_full[s], hs * ATT_HD + 64, row0, b);
+        tma_load_3d(d2, &tmT2, &t_full[s], hs * ATT_HD, row0, b);
+        tma_load_3d(d2 + STR_CHUNK, &tmT2, &t_full[s], hs * ATT_HD + 64, row0, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_xy = make_idesc_bf16(128, SUB, 0, 0);
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, ATT_HD, 0, 1);
+      const uint32_t r1 = smem_u32(sR1), r2 = smem_u32(sR2), pt = smem_u32(sPT), dst = smem_u32(sDST);
+      auto issue_xy = [&](int t) {
+        const int s = t & 1;
+        mbar_wait(&t_full[s], (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t1 = smem_u32(sT + s * 2 * STR_BYTES), t2 = t1 + STR_BYTES;
+        const uint32_t x_t = tmem_base + s * 128, y_t = x_t + 64;
+#pragma unroll
+        for (int k = 0; k < ATT_HD / 16; ++k) {
+          const uint32_t ro = (k >> 2) * RES_CHUNK + (k & 3) * 32, so = (k >> 2) * STR_CHUNK + (k & 3) * 32;
+          umma_ss(x_t, make_sdesc_sw128(r1 + ro, 0, 1024), make_sdesc_sw128(t1 + so, 0, 1024), idesc_xy, k > 0);
+        }
+#pragma unroll
+        for (int k = 0; k < ATT_HD / 16; ++k) {
+          const uint32_t ro = (k >> 2) * RES_CHUNK + (k & 3) * 32, so = (k >> 2) * STR_CHUNK + (k & 3) * 32;
+          umma_ss(y_t, make_sdesc_sw128(r2 + ro, 0, 1024), make_sdesc_sw128(t2 + so, 0, 1024), idesc_xy, k > 0);
+        }
+        umma_commit(&xy_full[s]);
+      };
+      mbar_wait(r_full, 0);
+      issue_xy(0);
+      for (int t = 0; t < n; ++t) {
+        if (t + 1 < n) issue_xy(t + 1);
+        const int s = t & 1;
+        mbar_wait(pds_full, t & 1);
+        tc_fence_after();
+        const uint32_t t1 = smem_u32(sT + s * 2 * STR_BYTES), t2 = t1 + STR_BYTES;
+#pragma unroll
+        for (int k = 0; k < SUB / 16; ++k) {
+          if (DKDV) {
+            // dV += Pᵀ·dO   (B = dO tile, MN-major: hd contiguous)      dK += dSᵀ·Q
+            umma_ss(tmem_acc1, make_sdesc_sw128(pt + k * 32, 0, 1024), make_sdesc_sw128(t2 + k * 2048, STR_CHUNK, 1024),
+                    idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
+            umma_ss(tmem_acc2, make_sdesc_sw128(dst + k * 32, 0, 1024), make_sdesc_sw128(t1 + k * 2048, STR_CHUNK, 1024),
+                    idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
+          } else {
+            // dQ += dS·K
+            umma_ss(tmem_acc1, make_sdesc_sw128(dst + k * 32, 0, 1024), make_sdesc_sw128(t1 + k * 2048, STR_CHUNK, 1024),
+                    idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&t_empty[s]);
+        umma_commit(acc_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax-grad warps: thread = resident row =====================
+    const uint32_t quad = warp & 3u;
+    const uint32_t r = quad * 32 + lane;
+    const int tid = int(threadIdx.x) - 64;
+    const int self_pos = r0 + int(r);
+    const int32_t* docb = p.doc + int64_t(b) * p.T;
+    const int32_t self_doc = (self_pos < p.T) ? docb[self_pos] : 0;
+    const int32_t res_first = docb[r0];                                            // uniform
+    const int32_t res_last = (r0 + ATT_BLK - 1 < p.T) ? docb[r0 + ATT_BLK - 1] : 0;  // uniform
+    const uint32_t lane_sel = (quad * 32u) << 16;
+    float self_lse2 = 0.f, self_delta = 0.f;
+    if (!DKDV) {
+      const int64_t idx = (int64_t(b) * p.H + hy) * p.T + self_pos;
+      self_lse2 = (self_pos < p.T) ? p.lse[idx] * 1.4426950408889634f : __int_as_float(0x7f800000);
+      self_delta = (self_pos < p.T) ? p.delta[idx] : 0.f;
+    }
+
+    for (int t = 0; t < n; ++t) {
+      const int hs = iter_head(t), c0 = iter_row0(t);
+      const int sblk = c0 / ATT_BLK;
+      // pair of 128-blocks is one document strictly off the diagonal -> no mask arithmetic
+      bool full;
+      if (DKDV) full = meta.canonical && (sblk > blk) && (res_first > 0) && (c0 / ATT_BLK * ATT_BLK + ATT_BLK - 1 < p.T) &&
+                       (docb[sblk * ATT_BLK + ATT_BLK - 1] == res_first);
+      else      full = meta.canonical && (sblk < blk) && (res_last > 0) && (docb[sblk * ATT_BLK] == res_last);
+      mbar_wait(&xy_full[t & 1], (t >> 1) & 1);
+      tc_fence_after();
+      float* col = sCol + (t & 1) * 3 * SUB;
+      float* col_lse2 = col;
+      float* col_delta = col + SUB;
+      int32_t* col_doc = reinterpret_cast<int32_t*>(col + 2 * SUB);
+      {
+        const int c = tid & 63, pos = c0 + c;
+        if (tid < 64) {
+          col_doc[c] = (pos < p.T) ? docb[pos] : -2;
+          if (DKDV) col_lse2[c] = (pos < p.T) ? p.lse[(int64_t(b) * p.H + hs) * p.T + pos] * 1.4426950408889634f
+                                              : __int_as_float(0x7f800000);
+        } else if (DKDV) {
+          col_delta[c] = (pos < p.T) ? p.delta[(int64_t(b) * p.H + hs) * p.T + pos] : 0.f;
+        }
+      }
+      named_bar_sync(1, 128);
+
+      const uint32_t x_t = tmem_base + (t & 1) * 128 + lane_sel, y_t = x_t + 64;
+      uint32_t pk[32], dk[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t xv[32], yv[32];
+        tmem_ld32(x_t + half * 32, xv);
+        tmem_ld32(y_t + half * 32, yv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float pe[2], de[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = half * 32 + i + e;
+            const int col_pos = c0 + c;
+            bool ok = true;
+            if (!full) {
+              const bool causal = DKDV ? (self_pos <= col_pos) : (col_pos <= self_pos);
+              ok = causal && (col_doc[c] == self_doc) && (self_doc > 0);
+            }
+            const float l2 = DKDV ? col_lse2[c] : self_lse2;
+            const float dl = DKDV ? col_delta[c] : self_delta;
+            const float pv = ok ? fast_exp2(fmaf(__uint_as_float(xv[i + e]), p.scale_log2, -l2)) : 0.f;
+            pe[e] = pv;
+            de[e] = pv * (__uint_as_float(yv[i + e]) - dl);
+          }
+          pk[(half * 32 + i) >> 1] = pack_bf16x2(pe[0], pe[1]);
+          dk[(half * 32 + i) >> 1] = pack_bf16x2(de[0], de[1]);
+        }
+      }
+      if (t > 0) mbar_wait(acc_done, (t - 1) & 1);  // previous accumulate MMAs have consumed the P/dS tiles
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (DKDV) *reinterpret_cast<uint4*>(sPT + sw128_off(r, u)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        *reinterpret_cast<uint4*>(sDST + sw128_off(r, u)) = make_uint4(dk[4 * u], dk[4 * u + 1], dk[4 * u + 2], dk[4 * u + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+    }
+
+    // ---- epilogue: accumulators -> bf16 -> smem staging (streamed-tile ring is idle now) -> TMA store ----
+    mbar_wait(acc_done, (n - 1) & 1);
+    tc_fence_after();
+    uint8_t* stage1 = sT;
+    uint8_t* stage2 = sT + RES_BYTES;
+#pragma unroll
+    for (int a = 0; a < (DKDV ? 2 : 1); ++a) {
+      const uint32_t acc_t = (a == 0 ? tmem_acc1 : tmem_acc2) + lane_sel;
+      uint8_t* stg = a == 0 ? stage1 : stage2;
+      const float mul = (DKDV && a == 0) ? 1.f : p.scale;  // dV unscaled; dK, dQ carry the softmax scale
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t o[32];
+        tmem_ld32(acc_t + c4 * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            w[e] = pack_bf16x2(__uint_as_float(o[u * 8 + 2 * e]) * mul, __uint_as_float(o[u * 8 + 2 * e + 1]) * mul);
+          const int colx = c4 * 32 + u * 8;
+          *reinterpret_cast<uint4*>(stg + (colx >> 6) * RES_CHUNK + sw128_off(r, (colx & 63) >> 3)) =
+              make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (tid == 0) {
+      tma_store_3d(&tmOut1, stage1, hy * ATT_HD, r0, b);
+      tma_store_3d(&tmOut1, stage1 + RES_CHUNK, hy * ATT_HD + 64, r0, b);
+      if (DKDV) {
+        tma_store_3d(&tmOut2, stage2, hy * ATT_HD, r0, b);
+        tma_store_3d(&tmOut2, stage2 + RES_CHUNK, hy * ATT_HD + 64, r0, b);
+      }
+      tma_store_commit();
+      tma_store_wait_read<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace tn
+
+using namespace tn;
+
+extern "C" int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                                const void* O, int64_t ldo, const void* dO, int64_t lddo, const float* lse, float* delta,
+                                void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv,
+                                const int32_t* doc_ids, const int32_t* meta, int B, int T, int H, int KV, float scale,
+                                tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(Q && K && V && O && dO && lse && delta && dQ && dK && dV && doc_ids && meta, "tn_attn_bwd_bf16: null pointer");
+  TN_REQUIRE(B > 0 && T > 0 && H > 0 && KV > 0 && H % KV == 0, "tn_attn_bwd_bf16: bad dims");
+  TN_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 &&
+                 lddk % 8 == 0 && lddv % 8 == 0, "tn_attn_bwd_bf16: strides must be multiples of 8");
+  const int nblk = (T + ATT_BLK - 1) / ATT_BLK;
+
+  {
+    const int64_t pairs = int64_t(B) * T * H;
+    const int64_t threads = pairs * 16;
+    attn_delta_kernel<<<unsigned((threads + 255) / 256), 256, 0, stream>>>(
+        static_cast<const bf16*>(O), ldo, static_cast<const bf16*>(dO), lddo, delta, B, T, H);
+    TN_CHECK_CUDA(cudaGetLastError());
+  }
+
+  CUtensorMap q128, q64, do128, do64, k128, k64, v128, v64, mdq, mdk, mdv;
+  int rc;
+#define TN_MAP(m, ptr, ld, heads, box)                                                                              \
+  if ((rc = encode_tmap_3d(&m, ptr, 2, uint64_t(heads) * ATT_HD, T, B, uint64_t(ld) * 2, uint64_t(T) * (ld) * 2, 64, box, \
+                           1, true)))                                                                               \
+    return rc;
+  TN_MAP(q128, Q, ldq, H, ATT_BLK) TN_MAP(q64, Q, ldq, H, SUB)
+  TN_MAP(do128, dO, lddo, H, ATT_BLK) TN_MAP(do64, dO, lddo, H, SUB)
+  TN_MAP(k128, K, ldk, KV, ATT_BLK) TN_MAP(k64, K, ldk, KV, SUB)
+  TN_MAP(v128, V, ldv, KV, ATT_BLK) TN_MAP(v64, V, ldv, KV, SUB)
+  TN_MAP(mdq, dQ, lddq, H, ATT_BLK) TN_MAP(mdk, dK, lddk, KV, ATT_BLK) TN_MAP(mdv, dV, lddv, KV, ATT_BLK)
+#undef TN_MAP
+
+  AttnBwdParams p{};
+  p.doc = doc_ids; p.meta = reinterpret_cast<const AttnMeta*>(meta); p.lse = lse; p.delta = delta;
+  p.B = B; p.T = T; p.H = H; p.KV = KV; p.nblk = nblk;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+
+  static bool configured = false;
+  if (!configured) {
+    TN_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::ALLOC));
+    TN_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::ALLOC));
+    configured = true;
+  }
+  {
+    AttnBwdParams pk = p;
+    pk.out1 = static_cast<bf16*>(dV); pk.ld1 = lddv; pk.out2 = static_cast<bf16*>(dK); pk.ld2 = lddk;
+    attn_bwd_kernel<true><<<dim3(nblk, KV, B), BWD_THREADS, BwdSmem::ALLOC, stream>>>(k128, v128, q64, do64, mdv, mdk, pk);
+    TN_CHECK_CUDA(cudaGetLastError());
+  }
+  {
+    AttnBwdParams pq = p;
+    pq.out1 = static_cast<bf16*>(dQ); pq.ld1 = lddq; pq.out2 = nullptr; pq.ld2 = 0;
+    attn_bwd_kernel<false><<<dim3(nblk, H, B), BWD_THREADS, BwdSmem::ALLOC, stream>>>(q128, do128, k64, v64, mdq, mdq, pq);
+    TN_CHECK_CUDA(cudaGetLastError());
+  }
+  return TN_OK;
+}

@@ -1,0 +1,339 @@
+// touchnet_b200 :: audio frontend (waveform -> fbank / log-mel -> stacked low-frame-rate features) on the GPU.
+//
+// Replaces, batched over utterances packed back to back in one buffer:
+//   audio_compute_fbank                touchnet/data/functions.py:117-134
+//       -> torchaudio.compliance.kaldi.fbank  ta:compliance/kaldi.py:514-645 (+ :44-84 framing, :154-217 window)
+//   audio_compute_log_mel_spectrogram  touchnet/data/functions.py:159-190 (whisper-style torch.stft path)
+//   audiofeat_stack                    touchnet/data/functions.py:258-286
+//
+// One CTA processes groups of 8 frames: warp w prepares frame w (DC removal, pre-emphasis, window | reflect
+// padding, window) into shared memory, then thread k evaluates DFT bin k for all 8 frames at once from a
+// shared cos/sin table (the transform length is tiny - 400 or 512 points - so a table-driven DFT with 16 FMAs
+// per 3 shared loads beats an FFT's synchronisation cost and handles n_fft = 400 without a mixed-radix plan),
+// power spectrum -> sparse mel filter rows -> log.  HBM traffic is the algorithmic minimum: every sample is read
+// once per frame that covers it (L1/L2 absorb the 2.5x overlap) and every feature is written once.
+#include <math.h>
+
+#include "../../include/touchnet_b200.h"
+#include "common.cuh"
+#include "host.h"
+
+namespace tn {
+
+constexpr int FE_THREADS = 288;   // >= max bins (257) rounded to warps; 9 warps
+constexpr int FE_FRAMES = 8;      // frames per group (one per warp 0..7)
+constexpr int FE_MAX_NFFT = 512;
+constexpr int FE_MAX_BINS = FE_MAX_NFFT / 2 + 1;
+constexpr int FE_MAX_MELS = 128;
+
+struct FrontendParams {
+  const void* wav;
+  int wav_is_i16;
+  const int64_t* utt_offsets;
+  const int64_t* frame_offsets;
+  int n_utts;
+  int64_t total_frames;
+  int frame_len, frame_shift, n_fft, n_bins, n_mels;
+  const float* window;       // [frame_len]
+  const float* mel_filters;  // [n_mels, n_bins]
+  float preemph;
+  float* out;      // [total_frames, n_mels]
+  float* utt_max;  // whisper mode
+};
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__device__ __forceinline__ int find_utt(const int64_t* __restrict__ frame_offsets, int n_utts, int64_t frame) {
+  int lo = 0, hi = n_utts - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (frame_offsets[mid] <= frame) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// MODE 0: kaldi fbank (snip_edges, DC removal, pre-emphasis, window, zero-pad to n_fft, log(max(x, eps)))
+// MODE 1: whisper log-mel (center + reflect padding, window length == n_fft, log10(max(x, 1e-10)), per-utt max)
+template <int MODE>
+__global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FrontendParams p) {
+  extern __shared__ float fe_smem[];
+  float2* tab = reinterpret_cast<float2*>(fe_smem);                       // [n_fft] (cos, sin)(2*pi*i/n_fft)
+  float* xs = fe_smem + 2 * FE_MAX_NFFT;                                  // [n_fft][8] frame-minor
+  float* ps = xs + FE_MAX_NFFT * FE_FRAMES;                               // [8][FE_MAX_BINS+3] power spectra
+  int* mel_lo = reinterpret_cast<int*>(ps + FE_FRAMES * (FE_MAX_BINS + 3));  // [n_mels]
+  int* mel_hi = mel_lo + FE_MAX_MELS;
+  constexpr int PS_LD = FE_MAX_BINS + 3;
+
+  const int tid = threadIdx.x;
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const int n_fft = p.n_fft, n_bins = p.n_bins;
+
+  for (int i = tid; i < n_fft; i += FE_THREADS) {
+    float s, c;
+    sincospif(2.0f * float(i) / float(n_fft), &s, &c);
+    tab[i] = make_float2(c, s);
+  }
+  // non-zero span of every (triangular) mel filter row
+  for (int m = tid; m < p.n_mels; m += FE_THREADS) {
+    const float* w = p.mel_filters + int64_t(m) * n_bins;
+    int lo = n_bins, hi = 0;
+    for (int k = 0; k < n_bins; ++k)
+      if (w[k] != 0.f) { lo = min(lo, k); hi = k + 1; }
+    mel_lo[m] = lo; mel_hi[m] = hi;
+  }
+  __syncthreads();
+
+  const int64_t n_groups = (p.total_frames + FE_FRAMES - 1) / FE_FRAMES;
+  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    // ---------------- stage 1: warp w prepares frame w ----------------
+    if (warp < FE_FRAMES) {
+      const int64_t frame = grp * FE_FRAMES + warp;
+      const bool valid = frame < p.total_frames;
+      int u = 0;
+      int64_t fi = 0, wav0 = 0, wav_n = 0;
+      if (valid) {
+        u = find_utt(p.frame_offsets, p.n_utts, frame);
+        fi = frame - p.frame_offsets[u];
+        wav0 = p.utt_offsets[u];
+        wav_n = p.utt_offsets[u + 1] - wav0;
+      }
+      constexpr int PER_LANE = (FE_MAX_NFFT + 31) / 32;  // 16
+      float v[PER_LANE];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) {
+        const int j = int(lane) + 32 * i;
+        float x = 0.f;
+        if (valid && j < p.frame_len) {
+          int64_t idx;
+          if (MODE == 0) {
+            idx = fi * p.frame_shift + j;  // snip_edges: every frame fits
+          } else {
+            idx = fi * p.frame_shift + j - n_fft / 2;  // center=True, reflect
+            if (idx < 0) idx = -idx;
+            if (idx >= wav_n) idx = 2 * (wav_n - 1) - idx;
+            if (idx < 0) idx = 0;
+          }
+          if (p.wav_is_i16) x = float(reinterpret_cast<const int16_t*>(p.wav)[wav0 + idx]);
+          else x = reinterpret_cast<const float*>(p.wav)[wav0 + idx] * (MODE == 0 ? 32768.f : 1.f);
+        }
+        v[i] = x;
+        sum += x;
+      }
+      if (MODE == 0) {
+        const float mean = warp_sum(sum) / float(p.frame_len);
+        // y[j] = (x[j]-mean) - c*(x[max(j-1,0)]-mean); neighbour j-1 lives in lane-1 (or lane 31 of slot i-1)
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) v[i] -= mean;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+          const float up = __shfl_up_sync(0xffffffffu, v[i], 1);
+          const float wrap = __shfl_sync(0xffffffffu, v[i > 0 ? i - 1 : 0], 31);
+          const float prev = (lane > 0) ? up : (i > 0 ? wrap : v[0]);  // replicate-left at j == 0
+          const int j = int(lane) + 32 * i;
+          float y = v[i] - p.preemph * prev;
+          y = (j < p.frame_len) ? y * p.window[j] : 0.f;
+          if (j < n_fft) xs[j * FE_FRAMES + warp] = y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+          const int j = int(lane) + 32 * i;
+          if (j < n_fft) xs[j * FE_FRAMES + warp] = (j < p.frame_len) ? v[i] * p.window[j] : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- stage 2: thread k -> DFT bin k of all 8 frames ----------------
+    if (tid < n_bins) {
+      float re[FE_FRAMES], im[FE_FRAMES];
+#pragma unroll
+      for (int f = 0; f < FE_FRAMES; ++f) { re[f] = 0.f; im[f] = 0.f; }
+      int idx = 0;
+      const int n_used = (MODE == 0) ? p.frame_len : n_fft;  // samples beyond frame_len are the zero padding
+      for (int n = 0; n < n_used; ++n) {
+        const float2 cs = tab[idx];
+        const float4 a = *reinterpret_cast<const float4*>(xs + n * FE_FRAMES);
+        const float4 b = *reinterpret_cast<const float4*>(xs + n * FE_FRAMES + 4);
+        re[0] = fmaf(a.x, cs.x, re[0]); im[0] = fmaf(a.x, cs.y, im[0]);
+        re[1] = fmaf(a.y, cs.x, re[1]); im[1] = fmaf(a.y, cs.y, im[1]);
+        re[2] = fmaf(a.z, cs.x, re[2]); im[2] = fmaf(a.z, cs.y, im[2]);
+        re[3] = fmaf(a.w, cs.x, re[3]); im[3] = fmaf(a.w, cs.y, im[3]);
+        re[4] = fmaf(b.x, cs.x, re[4]); im[4] = fmaf(b.x, cs.y, im[4]);
+        re[5] = fmaf(b.y, cs.x, re[5]); im[5] = fmaf(b.y, cs.y, im[5]);
+        re[6] = fmaf(b.z, cs.x, re[6]); im[6] = fmaf(b.z, cs.y, im[6]);
+        re[7] = fmaf(b.w, cs.x, re[7]); im[7] = fmaf(b.w, cs.y, im[7]);
+        idx += tid;
+        if (idx >= n_fft) idx -= n_fft;
+      }
+#pragma unroll
+      for (int f = 0; f < FE_FRAMES; ++f) ps[f * PS_LD + tid] = re[f] * re[f] + im[f] * im[f];
+    }
+    __syncthreads();
+    // ---------------- stage 3: mel filters + log ----------------
+    for (int o = tid; o < FE_FRAMES * p.n_mels; o += FE_THREADS) {
+      const int f = o / p.n_mels, m = o - f * p.n_mels;
+      const int64_t frame = grp * FE_FRAMES + f;
+      if (frame < p.total_frames) {
+        const float* w = p.mel_filters + int64_t(m) * n_bins;
+        float acc = 0.f;
+        for (int k = mel_lo[m]; k < mel_hi[m]; ++k) acc = fmaf(ps[f * PS_LD + k], __ldg(w + k), acc);
+        float y;
+        if (MODE == 0) {
+          y = logf(fmaxf(acc, 1.1920928955078125e-07f));  // torch.finfo(float32).eps
+        } else {
+          y = log10f(fmaxf(acc, 1e-10f));
+          const int u = find_utt(p.frame_offsets, p.n_utts, frame);
+          atomic_max_float(p.utt_max + u, y);
+        }
+        p.out[frame * p.n_mels + m] = y;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void fill_kernel(float* x, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+
+__global__ void __launch_bounds__(256) logmel_finish_kernel(float* __restrict__ feats,
+                                                            const int64_t* __restrict__ frame_offsets,
+                                                            const float* __restrict__ utt_max, int n_utts,
+                                                            int64_t total_frames, int n_mels) {
+  const int64_t total = total_frames * n_mels;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t frame = i / n_mels;
+    const int u = find_utt(frame_offsets, n_utts, frame);
+    const float x = fmaxf(feats[i], utt_max[u] - 8.0f);
+    feats[i] = (x + 4.0f) / 4.0f;
+  }
+}
+
+// one warp per output row
+__global__ void __launch_bounds__(256) feat_stack_kernel(const float* __restrict__ feats,
+                                                         const int64_t* __restrict__ frame_offsets,
+                                                         const int64_t* __restrict__ out_offsets, int n_utts,
+                                                         int64_t total_out_rows, int n_mels, int stack, int stride,
+                                                         int normalize, float* __restrict__ out) {
+  const int64_t row = int64_t(blockIdx.x) * 8 + warp_id();
+  if (row >= total_out_rows) return;
+  const uint32_t lane = lane_id();
+  const int u = find_utt(out_offsets, n_utts, row);
+  const int64_t i = row - out_offsets[u];
+  const int64_t f0 = frame_offsets[u];
+  const int64_t T = frame_offsets[u + 1] - f0;
+  const int left = (stack - 1) / 2;
+  const int width = stack * n_mels;
+  float* dst = out + row * width;
+  float sum = 0.f;
+  for (int c = lane; c < width; c += 32) {
+    const int s = c / n_mels, m = c - s * n_mels;
+    int64_t src = i * stride + s - left;
+    src = src < 0 ? 0 : (src > T - 1 ? T - 1 : src);
+    const float x = feats[(f0 + src) * n_mels + m];
+    dst[c] = x;
+    sum += x;
+  }
+  if (!normalize) return;
+  const float mean = warp_sum(sum) / float(width);
+  float ss = 0.f;
+  __syncwarp();
+  for (int c = lane; c < width; c += 32) {
+    const float d = dst[c] - mean;
+    ss += d * d;
+  }
+  const float stdv = sqrtf(warp_sum(ss) / float(width - 1));  // unbiased, as torch.std
+  const float inv = 1.f / (stdv + 1e-5f);
+  for (int c = lane; c < width; c += 32) dst[c] = (dst[c] - mean) * inv;
+}
+
+static int launch_frontend(int mode, const FrontendParams& p, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * (2 * FE_MAX_NFFT + FE_MAX_NFFT * FE_FRAMES + FE_FRAMES * (FE_MAX_BINS + 3)) +
+                      sizeof(int) * 2 * FE_MAX_MELS;
+  const int64_t n_groups = (p.total_frames + FE_FRAMES - 1) / FE_FRAMES;
+  int64_t grid = int64_t(sm_count()) * 4;
+  if (grid > n_groups) grid = n_groups;
+  if (mode == 0) frontend_kernel<0><<<unsigned(grid), FE_THREADS, smem, stream>>>(p);
+  else frontend_kernel<1><<<unsigned(grid), FE_THREADS, smem, stream>>>(p);
+  TN_CHECK_CUDA(cudaGetLastError());
+  return TN_OK;
+}
+
+}  // namespace tn
+
+using namespace tn;
+
+extern "C" int tn_fbank_f32(const void* wav, int wav_is_i16, const int64_t* utt_offsets, const int64_t* frame_offsets,
+                            int n_utts, int64_t total_frames, int frame_len, int frame_shift, int n_fft,
+                            const float* window, const float* mel_filters, int n_mels, float preemph, float* out,
+                            tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(wav && utt_offsets && frame_offsets && window && mel_filters && out, "tn_fbank_f32: null pointer");
+  TN_REQUIRE(n_fft <= FE_MAX_NFFT && n_fft % 2 == 0 && frame_len <= n_fft && frame_len >= 2 && frame_shift > 0,
+             "tn_fbank_f32: unsupported geometry frame_len=%d n_fft=%d (max %d)", frame_len, n_fft, FE_MAX_NFFT);
+  TN_REQUIRE(n_mels > 0 && n_mels <= FE_MAX_MELS, "tn_fbank_f32: n_mels=%d out of range (max %d)", n_mels, FE_MAX_MELS);
+  if (total_frames == 0 || n_utts == 0) return TN_OK;
+  FrontendParams p{};
+  p.wav = wav; p.wav_is_i16 = wav_is_i16; p.utt_offsets = utt_offsets; p.frame_offsets = frame_offsets;
+  p.n_utts = n_utts; p.total_frames = total_frames; p.frame_len = frame_len; p.frame_shift = frame_shift;
+  p.n_fft = n_fft; p.n_bins = n_fft / 2 + 1; p.n_mels = n_mels; p.window = window; p.mel_filters = mel_filters;
+  p.preemph = preemph; p.out = out; p.utt_max = nullptr;
+  return launch_frontend(0, p, stream);
+}
+
+extern "C" int tn_logmel_power_f32(const float* wav, const int64_t* utt_offsets, const int64_t* frame_offsets,
+                                   int n_utts, int64_t total_frames, int n_fft, int hop, const float* window,
+                                   const float* mel_filters, int n_mels, float* out, float* utt_max,
+                                   tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(wav && utt_offsets && frame_offsets && window && mel_filters && out && utt_max,
+             "tn_logmel_power_f32: null pointer");
+  TN_REQUIRE(n_fft <= FE_MAX_NFFT && n_fft % 2 == 0 && hop > 0, "tn_logmel_power_f32: unsupported n_fft=%d", n_fft);
+  TN_REQUIRE(n_mels > 0 && n_mels <= FE_MAX_MELS, "tn_logmel_power_f32: n_mels=%d out of range", n_mels);
+  if (n_utts == 0) return TN_OK;
+  fill_kernel<<<(n_utts + 255) / 256, 256, 0, stream>>>(utt_max, n_utts, -INFINITY);
+  TN_CHECK_CUDA(cudaGetLastError());
+  if (total_frames == 0) return TN_OK;
+  FrontendParams p{};
+  p.wav = wav; p.wav_is_i16 = 0; p.utt_offsets = utt_offsets; p.frame_offsets = frame_offsets;
+  p.n_utts = n_utts; p.total_frames = total_frames; p.frame_len = n_fft; p.frame_shift = hop;
+  p.n_fft = n_fft; p.n_bins = n_fft / 2 + 1; p.n_mels = n_mels; p.window = window; p.mel_filters = mel_filters;
+  p.preemph = 0.f; p.out = out; p.utt_max = utt_max;
+  return launch_frontend(1, p, stream);
+}
+
+extern "C" int tn_logmel_finish_f32(float* feats, const int64_t* frame_offsets, const float* utt_max, int n_utts,
+                                    int64_t total_frames, int n_mels, tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(feats && frame_offsets && utt_max, "tn_logmel_finish_f32: null pointer");
+  if (total_frames == 0) return TN_OK;
+  const int64_t total = total_frames * n_mels;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
+  logmel_finish_kernel<<<unsigned(blocks), 256, 0, stream>>>(feats, frame_offsets, utt_max, n_utts, total_frames, n_mels);
+  TN_CHECK_CUDA(cudaGetLastError());
+  return TN_OK;
+}
+
+extern "C" int tn_feat_stack_f32(const float* feats, const int64_t* frame_offsets, const int64_t* out_offsets, int n_utts,
+                                 int64_t total_out_rows, int n_mels, int stack, int stride, int normalize, float* out,
+                                 tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(feats && frame_offsets && out_offsets && out, "tn_feat_stack_f32: null pointer");
+  TN_REQUIRE(stack >= 1 && stride >= 1 && n_mels >= 1, "tn_feat_stack_f32: bad stack/stride");
+  if (total_out_rows == 0) return TN_OK;
+  feat_stack_kernel<<<unsigned((total_out_rows + 7) / 8), 256, 0, stream>>>(feats, frame_offsets, out_offsets, n_utts,
+                                                                           total_out_rows, n_mels, stack, stride,
+                                                                           normalize, out);
+  TN_CHECK_CUDA(cudaGetLastError());
+  return TN_OK;
+}

@@ -1,0 +1,404 @@
+"""Host-side op layer: thin, allocation-only wrappers around the C ABI (include/touchnet_b200.h) and the autograd
+Functions built from them.  PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every FLOP and
+every byte moved on the hot path happens inside libtouchnet_b200.so.  There is no fallback: a missing library or a
+non-CUDA tensor raises.
+
+Reference call sites each op replaces are listed in include/touchnet_b200.h.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, name: str, dtype=None):
+    if not t.is_cuda:
+        raise _lib.TouchNetB200Error(f"{name} must be a CUDA tensor (touchnet_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.TouchNetB200Error(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    """View as [rows, cols] with unit inner stride (no copy unless the input is not row-contiguous)."""
+    t2 = t.reshape(-1, t.shape[-1])
+    if t2.stride(-1) != 1 or (t2.shape[0] > 1 and t2.stride(0) < t2.shape[1]):
+        t2 = t2.contiguous()
+    return t2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bf16 working copies of fp32 master weights (what FSDP2's MixedPrecisionPolicy does at all-gather time,
+# ref: touchnet/models/helper_func.py:163; at 1 GPU the reference stays fp32, SURVEY 9.1 - we compute in bf16 always)
+# ---------------------------------------------------------------------------------------------------------------
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(src, "src", torch.float32)
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=BF16, device=src.device)
+    _lib.call("tn_cast_f32_bf16", src.data_ptr(), out.data_ptr(), src.numel(), _st())
+    return out
+
+
+def bf16_weight(w: torch.Tensor) -> torch.Tensor:
+    """bf16 view of a parameter: the tensor itself if already bf16, else a cached cast keyed on the version counter."""
+    w = w.detach()
+    if w.dtype == BF16:
+        return w if w.is_contiguous() else w.contiguous()
+    cache = getattr(w, "_tn_bf16", None)
+    if cache is not None and cache[0] == w._version and cache[1].shape == w.shape and cache[1].device == w.device:
+        return cache[1]
+    out = cast_bf16(w, cache[1] if cache is not None and cache[1].shape == w.shape and cache[1].device == w.device else None)
+    w._tn_bf16 = (w._version, out)
+    return out
+
+
+def drop_bf16_cache(module: torch.nn.Module) -> None:
+    """Forget cached bf16 copies (bench.py calls this every step so the cast is inside the timed region)."""
+    for p in module.parameters():
+        if hasattr(p, "_tn_bf16"):
+            p._tn_bf16 = (-1, p._tn_bf16[1])
+        d = p.detach()
+        if hasattr(d, "_tn_bf16"):
+            d._tn_bf16 = (-1, d._tn_bf16[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# raw ops (no autograd)
+# ---------------------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out_f32: bool = False,
+         residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, M=None, N=None, K=None):
+    """D[M,N] = op(A)·op(B) (+R).  a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] or [K,N] (b_mn=True)."""
+    _chk(a, "a", BF16); _chk(b, "b", BF16)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    if M is None:
+        M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+        N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+        assert K == Kb, (a.shape, b.shape, a_mn, b_mn)
+    dt = torch.float32 if out_f32 else BF16
+    if out is None:
+        out = torch.empty((M, N), dtype=dt, device=a.device)
+    assert out.dtype == dt and out.stride(1) == 1
+    if residual is not None:
+        assert residual.dtype == dt and residual.stride(-1) == 1
+        residual = residual.reshape(M, N) if residual.dim() != 2 else residual
+    _lib.call("tn_gemm_bf16", a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
+              out.data_ptr(), out.stride(0), int(out_f32), None if residual is None else residual.data_ptr(),
+              0 if residual is None else residual.stride(0), M, N, K, _st())
+    return out
+
+
+def gemm_swiglu(x: torch.Tensor, wg: torch.Tensor, wu: torch.Tensor, need_gu: bool = True):
+    """G = x·Wgᵀ, U = x·Wuᵀ, H = silu(G)⊙U in one tcgen05 kernel (SwiGLU in the epilogue)."""
+    _chk(x, "x", BF16); _chk(wg, "wg", BF16); _chk(wu, "wu", BF16)
+    M, K = x.shape
+    N = wg.shape[0]
+    assert wg.shape == wu.shape == (N, K) and wg.stride(0) == wu.stride(0)
+    h = torch.empty((M, N), dtype=BF16, device=x.device)
+    g = torch.empty_like(h) if need_gu else None
+    u = torch.empty_like(h) if need_gu else None
+    _lib.call("tn_gemm_swiglu_bf16", x.data_ptr(), x.stride(0), wg.data_ptr(), wu.data_ptr(), wg.stride(0),
+              None if g is None else g.data_ptr(), None if u is None else u.data_ptr(), h.data_ptr(), N, M, N, K, _st())
+    return g, u, h
+
+
+def swiglu_bwd(g, u, dh, dg_out=None, du_out=None):
+    M, N = g.shape
+    dg = torch.empty_like(g) if dg_out is None else dg_out
+    du = torch.empty_like(u) if du_out is None else du_out
+    _lib.call("tn_swiglu_bwd_bf16", g.data_ptr(), u.data_ptr(), dh.data_ptr(), dg.data_ptr(), du.data_ptr(), M, N,
+              g.stride(0), _st())
+    return dg, du
+
+
+def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, residual: Optional[torch.Tensor] = None):
+    """Returns (y, s, rstd): s = x (+ residual) is the tensor that was normalised."""
+    _chk(x, "x", BF16)
+    rows, d = x.shape
+    y = torch.empty_like(x)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    s = torch.empty_like(x) if residual is not None else x
+    w = w.detach()
+    _lib.call("tn_rmsnorm_fwd_bf16", x.data_ptr(), None if residual is None else residual.data_ptr(), w.data_ptr(),
+              int(w.dtype == torch.float32), s.data_ptr() if residual is not None else None, y.data_ptr(),
+              rstd.data_ptr(), rows, d, float(eps), _st())
+    return y, s, rstd
+
+
+_norm_partials = None
+
+
+def rmsnorm_bwd(s: torch.Tensor, dy: torch.Tensor, w: torch.Tensor, rstd: torch.Tensor,
+                ds_extra: Optional[torch.Tensor] = None):
+    """Returns (ds, dw) with ds = d/ds RMSNorm (+ ds_extra: the gradient arriving through the residual branch)."""
+    global _norm_partials
+    if _norm_partials is None:
+        _norm_partials = _lib.load().tn_rmsnorm_bwd_num_partials()
+    rows, d = s.shape
+    ds = torch.empty_like(s)
+    part = torch.empty((_norm_partials, d), dtype=torch.float32, device=s.device)
+    w = w.detach()
+    _lib.call("tn_rmsnorm_bwd_bf16", s.data_ptr(), dy.data_ptr(), None if ds_extra is None else ds_extra.data_ptr(),
+              w.data_ptr(), int(w.dtype == torch.float32), rstd.data_ptr(), ds.data_ptr(), part.data_ptr(),
+              _norm_partials, rows, d, _st())
+    n_used = min(rows, _norm_partials)
+    return ds, part[:n_used].sum(0)
+
+
+def rope_table(position_ids: torch.Tensor, inv_freq: torch.Tensor, scaling: float = 1.0):
+    """cos/sin tables [B*T, hd/2] bf16 for per-document positions."""
+    _chk(position_ids, "position_ids", torch.int64)
+    pos = position_ids.reshape(-1).contiguous()
+    inv = inv_freq.detach().to(device=pos.device, dtype=torch.float32).contiguous()
+    rows, half = pos.numel(), inv.numel()
+    cos = torch.empty((rows, half), dtype=BF16, device=pos.device)
+    sin = torch.empty_like(cos)
+    _lib.call("tn_rope_table", pos.data_ptr(), inv.data_ptr(), float(scaling), cos.data_ptr(), sin.data_ptr(), rows, half, _st())
+    return cos, sin
+
+
+def rope_apply_(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, head_dim: int, inverse: bool = False):
+    """In-place RoPE on x [rows, n_heads*head_dim] (row stride arbitrary)."""
+    _chk(x, "x", BF16)
+    rows = x.shape[0]
+    assert x.stride(1) == 1 and cos.shape == (rows, head_dim // 2)
+    _lib.call("tn_rope_apply_bf16", x.data_ptr(), x.stride(0), cos.data_ptr(), sin.data_ptr(), rows, n_heads, head_dim,
+              int(inverse), _st())
+    return x
+
+
+class AttnPlan:
+    """Per-step packing metadata shared by every layer: int32 document ids + per-block kv/q ranges, built on device."""
+
+    def __init__(self, doc_ids: torch.Tensor):
+        _chk(doc_ids, "attention_mask (document ids)")
+        assert doc_ids.dim() == 2
+        self.B, self.T = doc_ids.shape
+        self.doc = doc_ids.to(torch.int32).contiguous()
+        nblk = (self.T + 127) // 128
+        self.meta = torch.empty(self.B * nblk * 4 + self.B, dtype=torch.int32, device=doc_ids.device)
+        _lib.call("tn_attn_prep", self.doc.data_ptr(), self.meta.data_ptr(), self.B, self.T, _st())
+
+
+def attn_fwd(q, k, v, plan: AttnPlan, H: int, KV: int, scale: float):
+    """q [B*T, H*128], k/v [B*T, KV*128] (row strides arbitrary) -> o [B*T, H*128], lse [B,H,T]."""
+    B, T = plan.B, plan.T
+    o = torch.empty((B * T, H * 128), dtype=BF16, device=q.device)
+    lse = torch.empty((B, H, T), dtype=torch.float32, device=q.device)
+    _lib.call("tn_attn_fwd_bf16", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+              o.data_ptr(), o.stride(0), lse.data_ptr(), plan.doc.data_ptr(), plan.meta.data_ptr(), B, T, H, KV,
+              float(scale), _st())
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, do, lse, plan: AttnPlan, H: int, KV: int, scale: float):
+    B, T = plan.B, plan.T
+    dq = torch.empty((B * T, H * 128), dtype=BF16, device=q.device)
+    dk = torch.empty((B * T, KV * 128), dtype=BF16, device=q.device)
+    dv = torch.empty_like(dk)
+    delta = torch.empty((B, H, T), dtype=torch.float32, device=q.device)
+    if do.stride(1) != 1:
+        do = do.contiguous()
+    _lib.call("tn_attn_bwd_bf16", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+              o.data_ptr(), o.stride(0), do.data_ptr(), do.stride(0), lse.data_ptr(), delta.data_ptr(),
+              dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0),
+              plan.doc.data_ptr(), plan.meta.data_ptr(), B, T, H, KV, float(scale), _st())
+    return dq, dk, dv
+
+
+def embed_add(input_ids: Optional[torch.Tensor], embed: Optional[torch.Tensor], proj: Optional[torch.Tensor],
+              rows: int, d: int, nan_flag: Optional[torch.Tensor] = None):
+    """E = embed[input_ids] + proj (either may be None)."""
+    dev = (proj if proj is not None else input_ids).device
+    e = torch.empty((rows, d), dtype=BF16, device=dev)
+    emb = None if embed is None else embed.detach()
+    _lib.call("tn_embed_add_bf16", None if input_ids is None else input_ids.data_ptr(),
+              None if emb is None else emb.data_ptr(), int(emb is not None and emb.dtype == torch.float32),
+              None if proj is None else proj.data_ptr(), e.data_ptr(),
+              None if nan_flag is None else nan_flag.data_ptr(), rows, d, 0 if emb is None else emb.shape[0], _st())
+    return e
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# autograd Functions
+# ---------------------------------------------------------------------------------------------------------------
+def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """dW[N,K] = dyᵀ·x, in the parameter's dtype (fp32 master -> fp32 gradient straight from the TMEM accumulator)."""
+    return gemm(dy2, x2, a_mn=True, b_mn=True, out_f32=(w.dtype == torch.float32))
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x·Wᵀ (+ bias) (+ residual).  F.linear at hf:modeling_llama.py:251-289,182-184;
+    ref: touchnet/models/touch_audio/modeling_touch_audio.py:127 (projector)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, residual):
+        x2 = _rows2d(x)
+        if x2.dtype != BF16:
+            x2 = x2.to(BF16)
+        wb = bf16_weight(w)
+        r2 = None if residual is None else _rows2d(residual)
+        y = gemm(x2, wb, residual=r2)
+        if bias is not None:
+            y += bias.to(BF16)
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.x_shape = x.shape
+        ctx.x_dtype = x.dtype
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy2 = _rows2d(dy)
+        if dy2.dtype != BF16:
+            dy2 = dy2.to(BF16)
+        dx = dw = db = dr = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy2, bf16_weight(w), b_mn=True).view(ctx.x_shape).to(ctx.x_dtype)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dy2, x2, w)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.float().sum(0).to(w.dtype)
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dr = dy
+        return dx, dw, db, dr
+
+
+def linear(x, w, bias=None, residual=None):
+    return LinearFn.apply(x, w, bias, residual)
+
+
+class RMSNormFn(torch.autograd.Function):
+    """hf: LlamaRMSNorm.forward modeling_llama.py:62-67."""
+
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        x2 = _rows2d(x)
+        y, _, rstd = rmsnorm_fwd(x2, w, eps)
+        ctx.save_for_backward(x2, w, rstd)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, rstd = ctx.saved_tensors
+        ds, dw = rmsnorm_bwd(x2, _rows2d(dy), w, rstd)
+        return ds.view(dy.shape), dw.to(w.dtype), None
+
+
+def rms_norm(x, w, eps):
+    return RMSNormFn.apply(x, w, eps)
+
+
+class PackedAttentionFn(torch.autograd.Function):
+    """RoPE + block-causal document attention on projected q/k/v ([B*T, heads*128] GEMM outputs, rotated in place).
+    hf: apply_rotary_pos_emb :151-168 + flex_attention_forward (integrations/flex_attention.py:262-364)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, cos, sin, plan, H, KV, scale):
+        rope_apply_(q, cos, sin, H, 128)
+        rope_apply_(k, cos, sin, KV, 128)
+        o, lse = attn_fwd(q, k, v, plan, H, KV, scale)
+        ctx.save_for_backward(q, k, v, o, lse, cos, sin)
+        ctx.plan, ctx.H, ctx.KV, ctx.scale = plan, H, KV, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse, cos, sin = ctx.saved_tensors
+        dq, dk, dv = attn_bwd(q, k, v, o, do, lse, ctx.plan, ctx.H, ctx.KV, ctx.scale)
+        rope_apply_(dq, cos, sin, ctx.H, 128, inverse=True)
+        rope_apply_(dk, cos, sin, ctx.KV, 128, inverse=True)
+        return dq, dk, dv, None, None, None, None, None, None
+
+
+class SwiGLUFn(torch.autograd.Function):
+    """hmid = silu(x·Wgᵀ) ⊙ (x·Wuᵀ), one kernel.  hf: LlamaMLP.forward modeling_llama.py:182-184."""
+
+    @staticmethod
+    def forward(ctx, x, wg, wu):
+        x2 = _rows2d(x)
+        g, u, h = gemm_swiglu(x2, bf16_weight(wg), bf16_weight(wu))
+        ctx.save_for_backward(x2, wg, wu, g, u)
+        return h.view(*x.shape[:-1], wg.shape[0])
+
+    @staticmethod
+    def backward(ctx, dh):
+        x2, wg, wu, g, u = ctx.saved_tensors
+        dg, du = swiglu_bwd(g, u, _rows2d(dh))
+        dx = gemm(dg, bf16_weight(wg), b_mn=True)
+        dx = gemm(du, bf16_weight(wu), b_mn=True, residual=dx, out=dx)
+        return dx.view(*dh.shape[:-1], x2.shape[1]), _wgrad(dg, x2, wg), _wgrad(du, x2, wu)
+
+
+class DecoderLayerFn(torch.autograd.Function):
+    """One pre-norm decoder block as a single autograd node (hf: LlamaDecoderLayer.forward modeling_llama.py:303-333):
+    15 kernel launches forward, residual adds fused into the o_proj / down_proj GEMM epilogues, the residual-branch
+    gradient fused into the RMSNorm backward kernel.  Parameters stay separate nn.Linear weights (HF FQNs) so FSDP2 /
+    DCP / convert_* of the reference keep working (ref: touchnet/models/helper_func.py:134-202)."""
+
+    @staticmethod
+    def forward(ctx, x, ln1, wq, wk, wv, bq, bk, bv, wo, ln2, wg, wu, wd, cos, sin, plan, H, KV, eps):
+        x2 = _rows2d(x)
+        scale = 1.0 / math.sqrt(128)
+        h1, _, rstd1 = rmsnorm_fwd(x2, ln1, eps)
+        q = gemm(h1, bf16_weight(wq)); k = gemm(h1, bf16_weight(wk)); v = gemm(h1, bf16_weight(wv))
+        if bq is not None:
+            q += bq.to(BF16); k += bk.to(BF16); v += bv.to(BF16)
+        rope_apply_(q, cos, sin, H, 128)
+        rope_apply_(k, cos, sin, KV, 128)
+        o, lse = attn_fwd(q, k, v, plan, H, KV, scale)
+        x1 = gemm(o, bf16_weight(wo), residual=x2)
+        h2, _, rstd2 = rmsnorm_fwd(x1, ln2, eps)
+        g, u, hm = gemm_swiglu(h2, bf16_weight(wg), bf16_weight(wu))
+        out = gemm(hm, bf16_weight(wd), residual=x1)
+        ctx.save_for_backward(x2, ln1, wq, wk, wv, wo, ln2, wg, wu, wd, cos, sin, rstd1, h1, q, k, v, o, lse, x1, rstd2,
+                              h2, g, u, hm)
+        ctx.plan, ctx.H, ctx.KV, ctx.scale, ctx.has_bias = plan, H, KV, scale, bq is not None
+        return out.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x2, ln1, wq, wk, wv, wo, ln2, wg, wu, wd, cos, sin, rstd1, h1, q, k, v, o, lse, x1, rstd2, h2, g, u,
+         hm) = ctx.saved_tensors
+        H, KV = ctx.H, ctx.KV
+        d2 = _rows2d(dout)
+        if d2.dtype != BF16:
+            d2 = d2.to(BF16)
+        # ---- MLP ----
+        dhm = gemm(d2, bf16_weight(wd), b_mn=True)
+        dwd = _wgrad(d2, hm, wd)
+        dg, du = swiglu_bwd(g, u, dhm)
+        del dhm
+        dh2 = gemm(dg, bf16_weight(wg), b_mn=True)
+        dh2 = gemm(du, bf16_weight(wu), b_mn=True, residual=dh2, out=dh2)
+        dwg = _wgrad(dg, h2, wg)
+        dwu = _wgrad(du, h2, wu)
+        del dg, du
+        dx1, dln2 = rmsnorm_bwd(x1, dh2, ln2, rstd2, ds_extra=d2)
+        # ---- attention ----
+        do = gemm(dx1, bf16_weight(wo), b_mn=True)
+        dwo = _wgrad(dx1, o, wo)
+        dq, dk, dv = attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale)
+        rope_apply_(dq, cos, sin, H, 128, inverse=True)
+        rope_apply_(dk, cos, sin, KV, 128, inverse=True)
+        dh1 = gemm(dq, bf16_weight(wq), b_mn=True)
+        dh1 = gemm(dk, bf16_weight(wk), b_mn=True, residual=dh1, out=dh1)
+        dh1 = gemm(dv, bf16_weight(wv), b_mn=True, residual=dh1, out=dh1)
+        dwq = _wgrad(dq, h1, wq); dwk = _wgrad(dk, h1, wk); dwv = _wgrad(dv, h1, wv)
+        dbq = dbk = dbv = None
+        if ctx.has_bias:
+            dbq = dq.float().sum(0).to(wq.dtype); dbk = dk.float().sum(0).to(wq.dtype); dbv = dv.float().sum(0).to(wq.dtype)
+        dx, dln1 = rmsnorm_bwd(x2, dh1, ln1, rstd1, ds_extra=dx1)
+        return (dx.view(dout.shape), dln1.to(ln1.dtype), dwq, dwk, dwv, dbq, dbk, dbv, dwo, dln2.to(ln2.dtype), dwg, dwu,
+                dwd, None, None, None, None, None, None)

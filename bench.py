@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""bench.py - packed tokens/s of the TouchNet hot path on B200 (contract: see the task statement / DESIGN.md §6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one packed synthetic audio+text batch per GPU:
+    raw waveforms -> fbank -> stack/stride -> input_features            (csrc/frontend.cu)
+    TouchAudioForCausalLM forward (projector + 32 decoder layers + lm_head), pack-loss, backward
+                                                                         (csrc/gemm.cu, attn_*.cu, elementwise.cu)
+on the workload BASELINE.json's metric is quoted on: Llama-3-8B-ASR = TouchAudioForCausalLM around the Llama-3-8B text
+config, packed seq_len 8192, one row per GPU (weak scaling), bf16 compute with fp32 master weights and fp32 weight
+gradients.  `value` = tokens of all ranks / device time (CUDA events, max over ranks) with inputs resident in HBM;
+`e2e` = the same through the public module API with the step's inputs starting in pinned host memory (H2D inside the
+timed region) and the loss read back (D2H) every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+from types import SimpleNamespace as NS
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG2E = 1.4426950408889634
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seq-len", type=int, default=8192)
+    ap.add_argument("--batch", type=int, default=1, help="packed rows per GPU")
+    ap.add_argument("--layers", type=int, default=32, help="debug only: anything but 32 is not the named workload")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------------
+STACK, STRIDE, MEL = 5, 4, 80          # audio pretrain recipe (examples/audio/pretrain/wenetspeech/run.sh:57)
+
+
+def text_config(layers: int):
+    """Llama-3-8B shape (L=32, d=4096, H=32, KV=8, hd=128, ffn=14336, V=128256, theta 5e5 + llama3 scaling)."""
+    return NS(hidden_size=4096, intermediate_size=14336, num_hidden_layers=layers, num_attention_heads=32,
+              num_key_value_heads=8, head_dim=128, vocab_size=128256, rms_norm_eps=1e-5, rope_theta=500000.0,
+              rope_scaling={"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                            "original_max_position_embeddings": 8192},
+              attention_bias=False, tie_word_embeddings=False, initializer_range=0.02, model_type="llama",
+              pad_token_id=0)
+
+
+def asr_config(layers: int):
+    return NS(audio_config=NS(input_size=MEL * STACK), text_config=text_config(layers), pad_token_id=0)
+
+
+def make_host_batch(seed: int, B: int, T: int, vocab: int):
+    """One packed audio+text batch in pinned host memory: raw fp32 waveforms + the integer side of the layout."""
+    from touchnet_b200 import batching
+    buf, placed = batching.plan_audio_text_batch(seed, B, T, vocab, stride=STRIDE, max_s=30.0)
+    wav = torch.cat([u["waveform"] for u in placed]).contiguous().pin_memory()
+    host = {
+        "wav": wav,
+        "input_ids": buf["input_ids"].pin_memory(),
+        "labels": buf["labels"].pin_memory(),
+        "position_ids": buf["position_ids"].pin_memory(),
+        "attention_mask": buf["attention_mask"].pin_memory(),
+        "sentence_lens": buf["sentence_lens"].pin_memory(),
+    }
+    meta = {
+        "lens": [int(u["waveform"].numel()) for u in placed],
+        "dst_rows": [u["row"] * T + u["offset"] for u in placed],
+        "frames": [u["frames"] for u in placed],
+        "num_sentence": int(buf["num_sentence"]),
+        "doc_lens": [],
+    }
+    doc = buf["attention_mask"]
+    for b in range(B):
+        ids = doc[b][doc[b] > 0]
+        if ids.numel():
+            meta["doc_lens"] += torch.bincount(ids)[1:].tolist()
+    meta["nonpad_tokens"] = int((doc > 0).sum())
+    return host, meta
+
+
+def to_device(host: dict, dev) -> dict:
+    return {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+
+
+def h2d_bytes(host: dict) -> int:
+    return int(sum(v.numel() * v.element_size() for v in host.values()))
+
+
+def run_step(model, d: dict, meta: dict, B: int, T: int):
+    """frontend -> forward -> pack loss -> backward.  Returns the loss tensor (device)."""
+    from touchnet_b200 import frontend
+    feats = torch.zeros((B * T, MEL * STACK), dtype=torch.float32, device=d["wav"].device)
+    fb, frames = frontend.fbank_batch(d["wav"], meta["lens"], num_mel_bins=MEL)
+    frontend.stack_batch(fb, frames, STACK, STRIDE, True, into=feats, dst_rows=meta["dst_rows"])
+    out = model(input_ids=d["input_ids"], input_features=feats.view(B, T, -1), attention_mask=d["attention_mask"],
+                position_ids=d["position_ids"])
+    logits = out.logits
+    V = logits.shape[-1]
+    # pack loss next to the path (ref: touchnet/loss/cross_entropy.py:12-50): torch ops, not part of the v1 kernel set
+    ce = F.cross_entropy(logits.float().view(-1, V), d["labels"].view(-1), reduction="none", ignore_index=-100)
+    loss = (ce / d["sentence_lens"].view(-1).float()).sum() / max(meta["num_sentence"], 1)
+    loss.backward()
+    return loss.detach()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# measurement helpers
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # samples under load only (the sampler also sees the idle edges of the region)
+        loaded = [x for x in sm if mx is None or x > 0.4 * mx] or sm
+        med = loaded[len(loaded) // 2] if loaded else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class GemmTimer:
+    """CUDA events around every GEMM launch of the timed region (launching stream), summed afterwards."""
+
+    def __init__(self):
+        self.pairs = []
+        self._open = None
+
+    def __call__(self, name, phase, args):
+        if name not in ("tn_gemm_bf16", "tn_gemm_swiglu_bf16"):
+            return
+        if phase == "pre":
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            if name == "tn_gemm_bf16":
+                M, N, K = args[11], args[12], args[13]
+                flops = 2.0 * M * N * K
+            else:
+                M, N, K = args[9], args[10], args[11]
+                flops = 4.0 * M * N * K
+            self._open = (e, flops)
+        else:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.pairs.append((self._open[0], e1, self._open[1]))
+
+    def summary(self):
+        ms = sum(a.elapsed_time(b) for a, b, _ in self.pairs)
+        fl = sum(f for _, _, f in self.pairs)
+        return ms, fl, len(self.pairs)
+
+
+def attn_flops_fwd_per_layer(doc_lens, H=32, hd=128):
+    """mask-exact: 4*H*hd*sum n_i(n_i+1)/2."""
+    return 4.0 * H * hd * sum(n * (n + 1) / 2 for n in doc_lens)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"bf16_sustained": j["bf16_tflops_sustained"], "bf16_burst": j["bf16_tflops"], "hbm": j["hbm_gbs"],
+                "source": "measured"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle port of the reference's CPU path on a bounded sample
+# ---------------------------------------------------------------------------------------------------------------
+CPU_SAMPLE_T = 2048
+
+
+def cpu_reference_step(state):
+    """One bounded sample: 1 of the 32 decoder layers, forward + backward, fp32, one packed row of CPU_SAMPLE_T tokens with
+    the dense document mask (the only attention the reference runs on CPU, tests/touchnet/models/test_llama.py:93-95),
+    plus the fbank+stack frontend for the audio of that row.  Returns seconds."""
+    from oracle import frontend_oracle as fo
+    from oracle import model_oracle as mo
+    cfg, params, x, cos, sin, allow, wavs = state
+    t0 = time.perf_counter()
+    for w in wavs:
+        fo.stack(fo.fbank(w), STACK, STRIDE, True)
+    xx = x.clone().requires_grad_(True)
+    y = mo.decoder_layer(xx, params, "model.layers.0.", cfg, cos, sin, allow)
+    y.square().mean().backward()
+    return time.perf_counter() - t0
+
+
+def cpu_reference_setup(seed=2025):
+    from oracle import model_oracle as mo
+    from touchnet_b200 import batching
+    torch.set_num_threads(os.cpu_count() or 1)
+    tc = text_config(1)
+    cfg = mo.OracleConfig(hidden_size=tc.hidden_size, intermediate_size=tc.intermediate_size, num_hidden_layers=1,
+                          num_attention_heads=32, num_key_value_heads=8, head_dim=128, vocab_size=8,
+                          rope_theta=tc.rope_theta, rope_scaling=tc.rope_scaling)
+    g = torch.Generator().manual_seed(seed)
+    d, f = cfg.hidden_size, cfg.intermediate_size
+    L = "model.layers.0."
+    params = {L + "self_attn.q_proj.weight": torch.randn(4096, d, generator=g) * 0.02,
+              L + "self_attn.k_proj.weight": torch.randn(1024, d, generator=g) * 0.02,
+              L + "self_attn.v_proj.weight": torch.randn(1024, d, generator=g) * 0.02,
+              L + "self_attn.o_proj.weight": torch.randn(d, 4096, generator=g) * 0.02,
+              L + "mlp.gate_proj.weight": torch.randn(f, d, generator=g) * 0.02,
+              L + "mlp.up_proj.weight": torch.randn(f, d, generator=g) * 0.02,
+              L + "mlp.down_proj.weight": torch.randn(d, f, generator=g) * 0.02,
+              L + "input_layernorm.weight": torch.ones(d), L + "post_attention_layernorm.weight": torch.ones(d)}
+    for p in params.values():
+        p.requires_grad_(True)
+    buf, placed = batching.plan_audio_text_batch(seed, 1, CPU_SAMPLE_T, 128256, stride=STRIDE, max_s=30.0)
+    doc, pos = buf["attention_mask"], buf["position_ids"]
+    inv, sc = mo.rope_inv_freq(cfg)
+    cos, sin = mo.rope_cos_sin(pos, inv, sc, torch.float32)
+    allow = mo.doc_causal_allow(doc)
+    x = torch.randn(1, CPU_SAMPLE_T, d, generator=g)
+    wavs = [u["waveform"].numpy() for u in placed]
+    return (cfg, params, x, cos, sin, allow, wavs)
+
+
+def cpu_tokens_per_s(sec_per_sample: float) -> float:
+    """Extrapolation stated in the sample string: 32 layers cost 32x the measured layer; embeddings/lm_head/loss not
+    charged to the CPU arm (favours the CPU)."""
+    return CPU_SAMPLE_T / (32.0 * sec_per_sample)
+
+
+CPU_SAMPLE_DESC = (f"oracle port (fp32 torch, all host threads): fbank+stack of one packed row's audio + 1 of 32 decoder "
+                   f"layers fwd+bwd on a {CPU_SAMPLE_T}-token packed row with the dense document mask; tokens/s = "
+                   f"{CPU_SAMPLE_T} / (32 x t_sample); embeddings, lm_head and loss not charged")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    state = cpu_reference_setup()
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_step(state)
+    ts = [cpu_reference_step(state) for _ in range(args.steps)]
+    sec = sum(ts) / len(ts)
+    val = cpu_tokens_per_s(sec)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": "packed_tokens_per_sec", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE_DESC},
+            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {"workload": f"Llama-3-8B-ASR (TouchAudioForCausalLM, Llama-3-8B text config L={args.layers} d=4096 H=32 KV=8 "
+                        f"ffn=14336 V=128256, projector {MEL * STACK}->4096), audio+text packed rows, fbank80 stack{STACK}/"
+                        f"stride{STRIDE} frontend on GPU, fwd+bwd, fp32 master weights + fp32 weight grads",
+            "global_batch": args.batch * n, "seq_len": args.seq_len,
+            "parallelism": "single GPU" if n == 1 else f"FSDP2 dp_shard={n} (bf16 params / fp32 reduce)",
+            "l2_policy": "inputs larger than L2: every step streams >16 GB of weights through a 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# main arm
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: touchnet_b200 has no CPU path")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+
+    from touchnet_b200 import _lib, modeling, ops
+    _lib.load()
+    B, T = args.batch, args.seq_len
+    cfg = asr_config(args.layers)
+
+    torch.manual_seed(2025)
+    with torch.device(dev):
+        model = modeling.B200TouchAudioForCausalLM(cfg)
+    with torch.no_grad():                     # HF init: normal(0, 0.02), norms = 1 (fp32 master weights)
+        for p in model.parameters():
+            if p.dim() == 2:
+                p.normal_(0.0, 0.02)
+    if world > 1:
+        from torch.distributed.fsdp import MixedPrecisionPolicy, fully_shard
+        from torch.distributed.device_mesh import init_device_mesh
+        mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("dp_shard",))
+        mp = MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.float32)
+        layers = model.language_model.model.layers       # ref: touchnet/models/helper_func.py:134-202 apply_fsdp
+        for i, layer in enumerate(layers):
+            fully_shard(layer, mesh=mesh, mp_policy=mp, reshard_after_forward=(i < len(layers) - 1))
+        fully_shard(model, mesh=mesh, mp_policy=mp, reshard_after_forward=True)
+    model.train()
+
+    host, meta = make_host_batch(2025 + rank, B, T, cfg.text_config.vocab_size)
+    resident = to_device(host, dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(inputs):
+        model.zero_grad(set_to_none=True)
+        ops.invalidate_bf16_cache()          # the fp32->bf16 weight cast is part of every step
+        return run_step(model, inputs, meta, B, T)
+
+    # ---------------- device-resident arm ----------------
+    for _ in range(max(args.warmup, 3)):
+        one_step(resident)
+    barrier()
+    gt = GemmTimer()
+    _lib._hooks.append(gt)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = one_step(resident)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    _lib._hooks.remove(gt)
+    launches = _lib.launch_count - launches0
+    ms = e0.elapsed_time(e1)
+    gemm_ms, gemm_flops, gemm_n = gt.summary()
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    tokens_per_step = B * T * world
+    value = tokens_per_step * args.steps / (ms * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---------------- end-to-end arm: pinned host inputs, H2D inside, loss read back every step ----------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            float(one_step(to_device(host, dev)).item())
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            l = one_step(to_device(host, dev))
+            _ = float(l.item())                                  # D2H of the step's result
+        t1.record()
+        barrier()
+        ms2 = t0.elapsed_time(t1)
+        if dist is not None:
+            t = torch.tensor([ms2], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        e2e = {"value": tokens_per_step * args.steps / (ms2 * 1e-3), "unit": "tokens/s",
+               "h2d_bytes_per_step": h2d_bytes(host), "d2h_bytes_per_step": 4}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    n_layers = args.layers
+    attn_fwd = attn_flops_fwd_per_layer(meta["doc_lens"]) * n_layers
+    line = {
+        "metric": "packed_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": gemm_tflops / peaks["bf16_sustained"], "traffic": None,
+                     "kernel": "tn::gemm_kernel<BN,A_MN,B_MN,EPI> (all GEMM launches of the timed region)",
+                     "launches": gemm_n, "share_of_step": gemm_ms / ms if ms > 0 else None,
+                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); burst {peaks['bf16_burst']}"},
+        "extras": {"nonpad_tokens_per_step_rank0": meta["nonpad_tokens"], "docs_rank0": len(meta["doc_lens"]),
+                   "attn_fwd_tflop_mask_exact_per_step_rank0": attn_fwd / 1e12, "loss": final_loss,
+                   "model_tflop_per_step_rank0": gemm_flops / args.steps / 1e12,
+                   "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        state = cpu_reference_setup()
+        cpu_reference_step(state)
+        ts = [cpu_reference_step(state) for _ in range(2)]
+        sec = sum(ts) / len(ts)
+        line["cpu_baseline"] = {"value": cpu_tokens_per_s(sec), "unit": "tokens/s", "cores": torch.get_num_threads(),
+                                "kind": "port", "sample": CPU_SAMPLE_DESC}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

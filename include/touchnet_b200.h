@@ -115,7 +115,10 @@ int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, con
  *     max-8 clamp, (x+4)/4).  Two passes: tn_logmel_power writes log10 mel + per-utterance max (atomic), then
  *     tn_logmel_finish applies the clamp/affine in place.
  *   tn_feat_stack: touchnet/data/functions.py:258-286 audiofeat_stack (left/right replicate padding, stack/stride,
- *     optional per-row mean / unbiased-std normalisation).
+ *     optional per-row mean / unbiased-std normalisation).  dst_row0 == NULL: rows are written packed back to back;
+ *     otherwise utterance u's rows go to out[(dst_row0[u] + i) * out_ld ...], i.e. straight into the
+ *     input_features [B*T, F] buffer at the positions batch_pairaudio_pairtext_packed assigns
+ *     (touchnet/models/touch_audio/processing_touch_audio.py:200).
  */
 int tn_fbank_f32(const void* wav, int wav_is_i16, const int64_t* utt_offsets, const int64_t* frame_offsets, int n_utts,
                  int64_t total_frames, int frame_len, int frame_shift, int n_fft, const float* window,
@@ -127,7 +130,7 @@ int tn_logmel_finish_f32(float* feats, const int64_t* frame_offsets, const float
                          int64_t total_frames, int n_mels, tn_stream_t stream);
 int tn_feat_stack_f32(const float* feats, const int64_t* frame_offsets, const int64_t* out_offsets, int n_utts,
                       int64_t total_out_rows, int n_mels, int stack, int stride, int normalize, float* out,
-                      tn_stream_t stream);
+                      const int64_t* dst_row0, int64_t out_ld, tn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Small fused elementwise helpers on the path.

@@ -1,0 +1,126 @@
+"""GPU parity: packed-document attention (forward + backward) through the C ABI vs the oracle's dense-mask attention
+(oracle/model_oracle.py::attention, pinned to HF eager / FlexAttention semantics).
+Tolerance (bf16 kernel vs fp32 oracle on the same bf16 inputs): O and dQ/dK/dV relative L2 error < 2e-2 and max error
+< 3e-2*max|ref| + 3e-2; LSE abs error < 2e-3; padding rows exactly 0."""
+import math
+
+import pytest
+import torch
+
+from oracle import model_oracle as mo
+from tests.gpu_util import max_err, packed_doc_ids, rel_err, require_cuda
+from touchnet_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # name: (B, T, H, KV, lens_per_row)
+    "multi_doc_pad": (2, 512, 4, 2, [[100, 200, 150], [300, 50]]),
+    "single_doc_full_blocks": (1, 512, 2, 2, [[512]]),
+    "ragged_T": (2, 300, 2, 1, [[120, 180], [33, 90, 100]]),
+    "gqa4": (1, 384, 8, 2, [[200, 100, 84]]),
+    "long_doc": (1, 2048, 2, 1, [[1500, 500]]),
+    "tiny_docs": (1, 256, 2, 2, [[3, 1, 7, 2, 60, 1, 1, 50, 100]]),
+    "all_pad_row": (2, 256, 2, 1, [[256], []]),
+}
+
+
+def _run(name, custom_doc=None):
+    dev = require_cuda()
+    B, T, H, KV, lens = CASES[name]
+    torch.manual_seed(hash(name) % 1000)
+    doc, _ = packed_doc_ids(B, T, lens, dev)
+    if custom_doc is not None:
+        doc = custom_doc.to(dev)
+    q = torch.randn(B * T, H * 128, device=dev).bfloat16()
+    k = torch.randn(B * T, KV * 128, device=dev).bfloat16()
+    v = torch.randn(B * T, KV * 128, device=dev).bfloat16()
+    scale = 1 / math.sqrt(128)
+    plan = ops.AttnPlan(doc)
+    o, lse = ops.attn_fwd(q, k, v, plan, H, KV, scale)
+    torch.cuda.synchronize()
+    # oracle
+    qf = q.float().view(B, T, H, 128).transpose(1, 2).detach().requires_grad_(True)
+    kf = k.float().view(B, T, KV, 128).transpose(1, 2).detach().requires_grad_(True)
+    vf = v.float().view(B, T, KV, 128).transpose(1, 2).detach().requires_grad_(True)
+    allow = mo.doc_causal_allow(doc)
+    o_ref, lse_ref = mo.attention(qf, kf, vf, allow, scale)
+    o_ref2 = o_ref.reshape(B * T, H * 128)
+    valid = (doc > 0).reshape(-1)
+    assert torch.all(o[~valid] == 0), "padding query rows must be exactly zero (FlexAttention semantics)"
+    assert rel_err(o[valid].float(), o_ref2[valid]) < 2e-2, (name, rel_err(o[valid].float(), o_ref2[valid]))
+    assert max_err(o.float(), o_ref2) < 3e-2 * float(o_ref2.abs().max()) + 3e-2
+    vm = (doc > 0)[:, None, :].expand(B, H, T)
+    assert max_err(lse[vm], lse_ref[vm]) < 2e-3, max_err(lse[vm], lse_ref[vm])
+    assert torch.isinf(lse[~vm]).all()
+    # backward
+    do = torch.randn(B * T, H * 128, device=dev).bfloat16()
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, plan, H, KV, scale)
+    torch.cuda.synchronize()
+    o_ref.backward(do.float().view(B, T, H, 128))
+    dq_ref = qf.grad.transpose(1, 2).reshape(B * T, H * 128)
+    dk_ref = kf.grad.transpose(1, 2).reshape(B * T, KV * 128)
+    dv_ref = vf.grad.transpose(1, 2).reshape(B * T, KV * 128)
+    for nm, a, r in (("dq", dq, dq_ref), ("dk", dk, dk_ref), ("dv", dv, dv_ref)):
+        assert torch.isfinite(a.float()).all(), (name, nm)
+        assert rel_err(a.float(), r) < 2e-2, (name, nm, rel_err(a.float(), r))
+        assert max_err(a.float(), r) < 3e-2 * float(r.abs().max()) + 3e-2, (name, nm)
+    assert torch.all(dq[~valid] == 0)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_attention_parity(name):
+    _run(name)
+
+
+def test_attention_noncanonical_doc_ids():
+    """Ids that repeat non-contiguously (1,2,1,...) are legal for the reference's mask_mod; the kernel must fall back to
+    exact element-wise doc-id masking over the whole causal range."""
+    B, T = 1, 384
+    doc = torch.ones(B, T, dtype=torch.int64)
+    doc[0, 100:200] = 2
+    doc[0, 300:] = 0
+    doc[0, 350:] = 3   # a document after padding
+    CASES["noncanon"] = (B, T, 2, 1, [[T]])
+    _run("noncanon", custom_doc=doc)
+
+
+def test_attention_meta_ranges():
+    dev = require_cuda()
+    doc, _ = packed_doc_ids(1, 1024, [[300, 500, 100]], dev)       # docs [0,300) [300,800) [800,900), pad [900,1024)
+    plan = ops.AttnPlan(doc)
+    torch.cuda.synchronize()
+    meta = plan.meta[: 8 * 4].view(8, 4).cpu()
+    assert int(plan.meta[8 * 4]) == 1                              # canonical
+    # q block 2 (rows 256..383) starts in doc 1 (start 0) -> kv_lo = 0; q block 3 (384..511) is doc 2 (start 300) -> 2
+    assert meta[2].tolist()[:2] == [0, 3] and meta[3].tolist()[:2] == [2, 4]
+    assert meta[6].tolist()[:2] == [2, 7]                          # rows 768.. start in doc 2 (start 300)
+    assert meta[7].tolist()[:2] == [6, 8]                          # rows 896..899 are doc 3 (start 800)
+    # kv block 2 (cols 256..383): last valid col 383 is doc 2, run ends at 800 -> q blocks up to 6 (exclusive 7)
+    assert meta[2].tolist()[2] == 7 and meta[0].tolist()[2] == 3 and meta[7].tolist()[2] == 8
+
+
+def test_attention_autograd_function():
+    dev = require_cuda()
+    B, T, H, KV = 1, 256, 2, 1
+    doc, pos = packed_doc_ids(B, T, [[100, 156]], dev)
+    inv, sc = mo.rope_inv_freq(mo.OracleConfig(256, 8, 1, H, KV, 128, 8, rope_theta=10000.0))
+    cos, sin = ops.rope_table(pos, inv.to(dev), sc)
+    q = torch.randn(B * T, H * 128, device=dev).bfloat16().requires_grad_(True)
+    k = torch.randn(B * T, KV * 128, device=dev).bfloat16().requires_grad_(True)
+    v = torch.randn(B * T, KV * 128, device=dev).bfloat16().requires_grad_(True)
+    q_in, k_in = q.detach().clone(), k.detach().clone()
+    o = ops.PackedAttentionFn.apply(q.clone(), k.clone(), v, cos, sin, ops.AttnPlan(doc), H, KV, 1 / math.sqrt(128))
+    o.float().square().sum().backward()
+    # oracle: rope + attention, fp32
+    qf = q_in.float().view(B, T, H, 128).transpose(1, 2).requires_grad_(True)
+    kf = k_in.float().view(B, T, KV, 128).transpose(1, 2).requires_grad_(True)
+    vf = v.detach().float().view(B, T, KV, 128).transpose(1, 2).requires_grad_(True)
+    cr, sr = mo.rope_cos_sin(pos, inv.to(dev), sc, torch.float32)
+    qr, kr = mo.apply_rope(qf, kf, cr, sr)
+    o_ref, _ = mo.attention(qr, kr, vf, mo.doc_causal_allow(doc), 1 / math.sqrt(128))
+    o_ref.square().sum().backward()
+    assert rel_err(o.float(), o_ref.reshape(B * T, -1)) < 2e-2
+    assert rel_err(q.grad.float(), qf.grad.transpose(1, 2).reshape(B * T, -1)) < 3e-2
+    assert rel_err(k.grad.float(), kf.grad.transpose(1, 2).reshape(B * T, -1)) < 3e-2
+    assert rel_err(v.grad.float(), vf.grad.transpose(1, 2).reshape(B * T, -1)) < 3e-2

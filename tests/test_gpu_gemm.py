@@ -1,0 +1,79 @@
+"""GPU parity: tcgen05 GEMM family through the C ABI vs fp32 torch matmul on the same bf16 inputs.
+Tolerance: bf16 output rounding (2^-8 relative) + fp32 accumulation-order noise -> |err| <= 1e-2*max|ref| + 1e-2."""
+import pytest
+import torch
+
+from tests.gpu_util import require_cuda
+from touchnet_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(128, 256, 64), (256, 128, 256), (512, 1024, 512), (200, 264, 1040), (1024, 4096, 400), (384, 1024, 4096)]
+
+
+def _mk(M, N, K, dev):
+    torch.manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    b = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    return a, b
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_forward_dgrad_wgrad(M, N, K):
+    dev = require_cuda()
+    a, b = _mk(M, N, K, dev)
+    ref = a.float() @ b.float().t()
+    tol = 1e-2 * float(ref.abs().max()) + 1e-2
+    y = ops.gemm(a, b)                                           # forward  x·Wᵀ
+    assert float((y.float() - ref).abs().max()) < tol
+    dy = (torch.randn(M, N, device=dev) * 0.1).bfloat16()
+    dx = ops.gemm(dy, b, b_mn=True)                              # dgrad    dy·W
+    ref_dx = dy.float() @ b.float()
+    assert float((dx.float() - ref_dx).abs().max()) < 1e-2 * float(ref_dx.abs().max()) + 1e-2
+    dw = ops.gemm(dy, a, a_mn=True, b_mn=True, out_f32=True)     # wgrad    dyᵀ·x (fp32 straight from TMEM)
+    ref_dw = dy.float().t() @ a.float()
+    assert float((dw - ref_dw).abs().max()) < 1e-4 * float(ref_dw.abs().max()) + 1e-4
+    dwb = ops.gemm(dy, a, a_mn=True, b_mn=True)                  # wgrad, bf16 (FSDP2 mixed-precision path)
+    assert float((dwb.float() - ref_dw).abs().max()) < 1e-2 * float(ref_dw.abs().max()) + 1e-2
+
+
+def test_gemm_residual_and_accumulate():
+    dev = require_cuda()
+    a, b = _mk(512, 1024, 512, dev)
+    r = torch.randn(512, 1024, device=dev).bfloat16()
+    y = ops.gemm(a, b, residual=r)
+    ref = (a.float() @ b.float().t()).bfloat16().float() + r.float()
+    assert float((y.float() - ref).abs().max()) <= 2 ** -6 * float(ref.abs().max())
+    acc = torch.randn(1024, 512, device=dev)                      # fp32 gradient accumulation in place
+    dy = (torch.randn(512, 1024, device=dev) * 0.1).bfloat16()
+    want = acc + dy.float().t() @ a.float()
+    ops.gemm(dy, a, a_mn=True, b_mn=True, out_f32=True, residual=acc, out=acc)
+    assert float((acc - want).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 1024, 512), (200, 264, 1040), (256, 14336, 256)])
+def test_gemm_swiglu(M, N, K):
+    dev = require_cuda()
+    x, wg = _mk(M, N, K, dev)
+    wu = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    g, u, h = ops.gemm_swiglu(x, wg, wu)
+    g_ref = (x.float() @ wg.float().t())
+    u_ref = (x.float() @ wu.float().t())
+    assert float((g.float() - g_ref).abs().max()) < 1e-2 * float(g_ref.abs().max()) + 1e-2
+    assert float((u.float() - u_ref).abs().max()) < 1e-2 * float(u_ref.abs().max()) + 1e-2
+    # H must be exactly the unfused bf16 computation applied to the kernel's own (bf16) G and U
+    h_ref = (torch.nn.functional.silu(g.float()).bfloat16().float() * u.float()).bfloat16()
+    mism = (h != h_ref)
+    assert float(mism.float().mean()) < 1e-3, "SwiGLU epilogue deviates from silu(g)*u on its own outputs"
+    assert float((h.float() - h_ref.float()).abs().max()) <= 2 ** -6 * float(h_ref.float().abs().max()) + 1e-6
+
+
+def test_gemm_rejects_bad_arguments():
+    dev = require_cuda()
+    from touchnet_b200._lib import TouchNetB200Error
+    a = torch.zeros(128, 60, device=dev, dtype=torch.bfloat16)     # K=60: row stride not a multiple of 16 B
+    b = torch.zeros(128, 60, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(TouchNetB200Error):
+        ops.gemm(a, b)
+    with pytest.raises(TouchNetB200Error):
+        ops.gemm(torch.zeros(8, 8), torch.zeros(8, 8))             # CPU tensors: no CPU path

@@ -1,0 +1,183 @@
+"""GPU parity: the drop-in modules (touchnet_b200/modeling.py) vs the oracle restatement of the HF forward on identical
+weights and inputs, forward and backward, plus the structural contract (FQNs / state-dict keys / post_init attributes).
+
+Tolerances (bf16 compute vs the oracle run in bf16 with the HF rounding points, and vs the fp32 oracle):
+  logits: max |err| <= 3e-2 * max|ref| ; argmax identical wherever the oracle's top-2 margin exceeds 2x that error
+  parameter gradients: relative L2 error < 3e-2 per tensor vs fp32 autograd of the oracle."""
+import pytest
+import torch
+
+from oracle import model_oracle as mo
+from tests.gpu_util import max_err, packed_doc_ids, rel_err, require_cuda
+from touchnet_b200 import modeling
+
+pytestmark = pytest.mark.gpu
+
+
+class _Cfg:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def small_cfg(L=2, d=256, H=2, KV=1, ffn=512, V=512, rope_scaling=None, bias=False):
+    return _Cfg(hidden_size=d, intermediate_size=ffn, num_hidden_layers=L, num_attention_heads=H, num_key_value_heads=KV,
+                head_dim=128, vocab_size=V, rms_norm_eps=1e-5, rope_theta=500000.0, rope_scaling=rope_scaling,
+                attention_bias=bias, tie_word_embeddings=False, initializer_range=0.02, model_type="llama",
+                pad_token_id=0)
+
+
+def oracle_cfg(c, audio=0):
+    return mo.OracleConfig(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+                           num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
+                           num_key_value_heads=c.num_key_value_heads, head_dim=128, vocab_size=c.vocab_size,
+                           rms_norm_eps=c.rms_norm_eps, rope_theta=c.rope_theta, rope_scaling=c.rope_scaling,
+                           attention_bias=c.attention_bias, audio_input_size=audio)
+
+
+LLAMA3 = {"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+          "original_max_position_embeddings": 8192}
+
+
+def _check_logits(ours, ref, valid):
+    err = max_err(ours[valid].float(), ref[valid].float())
+    scale = float(ref[valid].float().abs().max())
+    assert err <= 3e-2 * scale + 1e-3, (err, scale)
+    top2 = ref[valid].float().topk(2, dim=-1).values
+    decisive = (top2[:, 0] - top2[:, 1]) > 2 * err
+    assert decisive.float().mean() > 0.5
+    assert torch.equal(ours[valid].float().argmax(-1)[decisive], ref[valid].float().argmax(-1)[decisive])
+
+
+@pytest.mark.parametrize("master_dtype", [torch.float32, torch.bfloat16])
+def test_llama_forward_backward_parity(master_dtype):
+    dev = require_cuda()
+    cfg = small_cfg(rope_scaling=LLAMA3)
+    B, T = 2, 384
+    torch.manual_seed(2025)
+    model = modeling.B200LlamaForCausalLM(cfg).to(dev)
+    model.post_init()
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 2:
+                p.normal_(0, 0.05)
+            else:
+                p.copy_(1 + 0.1 * torch.randn_like(p))
+    model.to(master_dtype)
+    doc, pos = packed_doc_ids(B, T, [[100, 200, 50], [384]], dev)
+    ids = torch.randint(0, cfg.vocab_size, (B, T), device=dev)
+    labels = torch.randint(0, cfg.vocab_size, (B, T), device=dev)
+    labels[doc == 0] = -100
+    out = model(input_ids=ids, attention_mask=doc, position_ids=pos)
+    logits = out.logits
+    assert logits.shape == (B, T, cfg.vocab_size) and logits.dtype == torch.bfloat16
+    loss = torch.nn.functional.cross_entropy(logits.float().view(-1, cfg.vocab_size), labels.view(-1), ignore_index=-100)
+    loss.backward()
+    # oracle on the bf16-rounded weights: fp32 math (gradient reference) and bf16 math (rounding-point reference)
+    params32 = {k: v.detach().bfloat16().float().requires_grad_(True) for k, v in model.state_dict().items()}
+    ocfg = oracle_cfg(cfg)
+    ref32 = mo.llama_forward(params32, ocfg, input_ids=ids, attention_mask=doc, position_ids=pos, dtype=torch.float32)
+    with torch.no_grad():
+        ref16 = mo.llama_forward({k: v.detach() for k, v in params32.items()}, ocfg, input_ids=ids, attention_mask=doc,
+                                 position_ids=pos, dtype=torch.bfloat16)
+    valid = doc > 0
+    _check_logits(logits, ref32, valid)
+    _check_logits(logits, ref16, valid)
+    loss_ref = torch.nn.functional.cross_entropy(ref32.view(-1, cfg.vocab_size), labels.view(-1), ignore_index=-100)
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
+    loss_ref.backward()
+    for name, p in model.named_parameters():
+        assert p.grad is not None and p.grad.dtype == master_dtype, name
+        assert torch.isfinite(p.grad.float()).all(), name
+        e = rel_err(p.grad.float(), params32[name].grad)
+        assert e < 3e-2, (name, e)
+
+
+def test_touch_audio_forward_backward_parity():
+    dev = require_cuda()
+    F_ = 400                                                        # 80 mel x stack 5
+    text = small_cfg(L=2, d=256, H=4, KV=4, bias=True)              # MHA + q/k/v bias: Qwen2-style text model (cfg 3)
+    text.model_type = "qwen2"
+    cfg = _Cfg(audio_config=_Cfg(input_size=F_), text_config=text, pad_token_id=0)
+    B, T = 2, 256
+    torch.manual_seed(7)
+    model = modeling.B200TouchAudioForCausalLM(cfg).to(dev)
+    model.post_init()
+    with torch.no_grad():
+        for n_, p in model.named_parameters():
+            if p.dim() == 2:
+                p.normal_(0, 0.05)
+            elif "bias" in n_:
+                p.normal_(0, 0.1)
+    doc, pos = packed_doc_ids(B, T, [[120, 100], [200, 56]], dev)
+    is_audio = torch.zeros(B, T, dtype=torch.bool, device=dev)
+    is_audio[0, :90] = True; is_audio[0, 120:200] = True; is_audio[1, :150] = True; is_audio[1, 200:240] = True
+    feats = torch.randn(B, T, F_, device=dev) * is_audio[..., None]
+    ids = torch.where(is_audio, torch.zeros(B, T, dtype=torch.int64, device=dev),
+                      torch.randint(3, text.vocab_size, (B, T), device=dev))
+    out = model(input_ids=ids, input_features=feats, attention_mask=doc, position_ids=pos, inputs_embeds=None)
+    assert out.attention_mask is doc                                # ref: modeling_touch_audio.py:151
+    logits = out.logits
+    logits.float().square().mean().backward()
+    model.raise_if_nan()
+    params32 = {k: v.detach().bfloat16().float().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = mo.touch_audio_forward(params32, oracle_cfg(text, audio=F_), input_ids=ids,
+                                 input_features=feats.bfloat16().float(), attention_mask=doc, position_ids=pos)
+    _check_logits(logits, ref, doc > 0)
+    # padding rows feed zeros forward in ours (FlexAttention semantics); restrict the loss to valid rows for gradients
+    model.zero_grad()
+    out = model(input_ids=ids, input_features=feats, attention_mask=doc, position_ids=pos)
+    (out.logits.float()[doc > 0]).square().mean().backward()
+    ref[doc > 0].square().mean().backward()
+    for name, p in model.named_parameters():
+        e = rel_err(p.grad.float(), params32[name].grad)
+        assert e < 3e-2, (name, e)
+    # NaN in the features -> ValueError("NaN in data."), as ref modeling_touch_audio.py:133-134
+    feats[0, 3, 5] = float("nan")
+    model(input_ids=ids, input_features=feats, attention_mask=doc, position_ids=pos)
+    with pytest.raises(ValueError, match="NaN in data"):
+        model.raise_if_nan()
+
+
+def test_plain_causal_defaults_and_text_only_batches():
+    dev = require_cuda()
+    cfg = small_cfg(L=1)
+    torch.manual_seed(3)
+    model = modeling.B200LlamaForCausalLM(cfg).to(dev)
+    model.post_init()
+    ids = torch.randint(0, cfg.vocab_size, (1, 200), device=dev)    # T not a multiple of 128, no mask, no positions
+    logits = model(input_ids=ids).logits
+    params = {k: v.detach().bfloat16().float() for k, v in model.state_dict().items()}
+    ref = mo.llama_forward(params, oracle_cfg(cfg), input_ids=ids)
+    _check_logits(logits, ref, torch.ones(1, 200, dtype=torch.bool, device=dev))
+
+
+def test_matches_hf_flex_attention_path():
+    """The thing the reference actually runs on a GPU: HF LlamaForCausalLM + flex_attention BlockMask
+    (make_flex_block_causal_mask).  Skipped only if this transformers/torch build cannot construct it."""
+    dev = require_cuda()
+    try:
+        from transformers import LlamaConfig, LlamaForCausalLM
+        from transformers.integrations.flex_attention import make_flex_block_causal_mask
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"transformers flex integration unavailable: {e}")
+    cfg = small_cfg(L=2, rope_scaling=LLAMA3)
+    hf_cfg = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                         num_key_value_heads=1, head_dim=128, vocab_size=512, rms_norm_eps=1e-5, rope_theta=500000.0,
+                         rope_scaling=dict(LLAMA3), tie_word_embeddings=False, attention_bias=False)
+    hf_cfg._attn_implementation = "flex_attention"
+    torch.manual_seed(11)
+    try:
+        hf = LlamaForCausalLM(hf_cfg).to(dev).to(torch.bfloat16).eval()
+        B, T = 1, 256
+        doc, pos = packed_doc_ids(B, T, [[100, 120]], dev)
+        ids = torch.randint(0, 512, (B, T), device=dev)
+        bm = make_flex_block_causal_mask(doc)
+        with torch.no_grad():
+            ref = hf(input_ids=ids, attention_mask=bm, position_ids=pos).logits
+    except Exception as e:
+        pytest.skip(f"HF flex_attention path not runnable in this image: {type(e).__name__}: {str(e)[:200]}")
+    ours = modeling.B200LlamaForCausalLM(cfg).to(dev)
+    missing = ours.load_state_dict(hf.state_dict(), strict=True)     # identical state-dict keys
+    ours.model.rotary_emb.inv_freq = hf.model.rotary_emb.inv_freq.float()
+    logits = ours(input_ids=ids, attention_mask=doc, position_ids=pos).logits
+    _check_logits(logits, ref, doc > 0)

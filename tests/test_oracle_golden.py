@@ -1,0 +1,114 @@
+"""CPU: the oracle (oracle/*.py) against the golden vectors generated from the reference itself
+(tests/golden/make_golden.py).  This is what pins the oracle; the GPU tests then compare the CUDA path with it."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frontend_oracle as fo
+from oracle import model_oracle as mo
+
+
+def power_close(ref_log, out_log, rtol=1e-4, floor=1e-6):
+    """fbank tolerance, stated in the power domain: |p - p_ref| <= rtol*p_ref + floor*max_frame(p_ref).
+    (log-domain differences in bins 60 dB below the frame peak are FFT rounding noise in any fp32 implementation.)"""
+    pr, po = np.exp(ref_log.astype(np.float64)), np.exp(out_log.astype(np.float64))
+    lim = rtol * pr + floor * pr.max(axis=1, keepdims=True)
+    return float((np.abs(pr - po) / lim).max())
+
+
+def test_fbank_oracle_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "frontend_fbank.npz"))
+    names = [k[6:] for k in g.files if k.startswith("fbank/")]
+    assert len(names) >= 5
+    for name in names:
+        out = fo.fbank(g["wav/" + name])
+        ref = g["fbank/" + name]
+        assert out.shape == ref.shape, name
+        assert power_close(ref, out) < 1.0, name
+
+
+def test_stack_oracle_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "frontend_fbank.npz"))
+    keys = [k for k in g.files if k.startswith("stack/")]
+    assert len(keys) >= 30
+    for k in keys:
+        _, name, cfg = k.split("/")
+        st, sd, nm = map(int, cfg.split("_"))
+        out = fo.stack(g["fbank/" + name], st, sd, bool(nm))
+        assert out.shape == g[k].shape, k
+        np.testing.assert_allclose(out, g[k], rtol=2e-4, atol=2e-4, err_msg=k)
+
+
+def test_logmel_oracle_matches_torch_stft_path(golden_dir):
+    g = np.load(os.path.join(golden_dir, "frontend_logmel.npz"))
+    for k in [k for k in g.files if k.startswith("logmel/")]:
+        _, name, nm = k.split("/")
+        out = fo.log_mel(g["wav/" + name], n_mels=int(nm))
+        assert out.shape == g[k].shape
+        np.testing.assert_allclose(out, g[k], atol=2e-4, rtol=0, err_msg=k)
+
+
+def test_slaney_filters_have_whisper_properties():
+    """librosa itself is absent (parity unpinned for this factor): check the published properties of whisper's
+    mel_filters - shape, Slaney area normalisation, triangular support, monotone centres."""
+    for n_mels in (80, 128):
+        w = fo.slaney_mel_filters(16000, 400, n_mels)
+        assert w.shape == (n_mels, 201) and (w >= 0).all()
+        centres = w.argmax(axis=1)
+        assert (np.diff(centres) >= 0).all()
+        # Slaney norm: each filter integrates to ~1 over Hz (bin width 40 Hz), away from the edges
+        area = w.sum(axis=1) * 40.0
+        if n_mels == 80:
+            assert np.allclose(area[5:-1], 1.0, atol=0.15)
+        else:  # 128 filters on 40 Hz bins: the low filters are narrower than a bin, only the mean area holds
+            assert abs(float(area.mean()) - 1.0) < 0.05
+    assert abs(float(fo.slaney_mel_filters(16000, 400, 80)[0].max()) - 0.02486) < 2e-3
+
+
+def _cfg_from_json(cj, **kw):
+    return mo.OracleConfig(hidden_size=cj["hidden_size"], intermediate_size=cj["intermediate_size"],
+                           num_hidden_layers=cj["num_hidden_layers"], num_attention_heads=cj["num_attention_heads"],
+                           num_key_value_heads=cj["num_key_value_heads"], head_dim=cj["head_dim"],
+                           vocab_size=cj["vocab_size"], rms_norm_eps=cj["rms_norm_eps"], rope_theta=cj["rope_theta"],
+                           rope_scaling=cj["rope_scaling"], tie_word_embeddings=cj["tie_word_embeddings"], **kw)
+
+
+def test_model_oracle_matches_hf_llama_and_reference_touch_audio(golden_dir):
+    g = np.load(os.path.join(golden_dir, "model_tiny.npz"))
+    cj = json.loads(bytes(g["config_json"]).decode())
+    cfg = _cfg_from_json(cj)
+    inv, _ = mo.rope_inv_freq(cfg)
+    assert torch.equal(inv, torch.from_numpy(g["llama/inv_freq"]))          # llama3 rope scaling, bit exact
+    doc = torch.from_numpy(g["llama/doc_ids"])
+    pos = torch.from_numpy(g["llama/position_ids"])
+    params = {k[9:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("llama_sd/")}
+    logits = mo.llama_forward(params, cfg, input_ids=torch.from_numpy(g["llama/input_ids"]), attention_mask=doc,
+                              position_ids=pos)
+    ref = torch.from_numpy(g["llama/logits"])
+    valid = doc > 0   # padding query rows: HF eager is undefined there, FlexAttention yields zeros
+    assert float((logits - ref)[valid].abs().max()) < 1e-5
+    assert torch.equal(logits[valid].argmax(-1), ref[valid].argmax(-1))      # bit-exact token indices
+
+    cfg_ta = _cfg_from_json(cj, audio_input_size=40)
+    params = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("ta_sd/")}
+    lg = mo.touch_audio_forward(params, cfg_ta, input_ids=torch.from_numpy(g["ta/input_ids"]),
+                                input_features=torch.from_numpy(g["ta/input_features"]), attention_mask=doc,
+                                position_ids=pos)
+    ref = torch.from_numpy(g["ta/logits"])
+    assert float((lg - ref)[valid].abs().max()) < 1e-5
+    assert torch.equal(lg[valid].argmax(-1), ref[valid].argmax(-1))
+
+
+def test_oracle_mask_semantics():
+    doc = torch.tensor([[1, 1, 2, 2, 2, 0, 0]])
+    allow = mo.doc_causal_allow(doc)[0]
+    assert allow[1, 0] and allow[1, 1] and not allow[0, 1]        # causal inside a document
+    assert not allow[2, 1] and allow[4, 2]                        # no attention across documents
+    assert not allow[5].any() and not allow[6].any()              # padding queries fully masked
+    assert not allow[:, 5].any()                                  # padding keys never attended
+    q = torch.randn(1, 2, 7, 8); k = torch.randn(1, 1, 7, 8); v = torch.randn(1, 1, 7, 8)
+    o, lse = mo.attention(q, k, v, mo.doc_causal_allow(doc), 8 ** -0.5)
+    assert torch.all(o[0, 5:] == 0) and torch.isinf(lse[0, :, 5:]).all()   # FlexAttention: exact zeros

@@ -35,7 +35,7 @@ _SIGNATURES = {
     "tn_fbank_f32": [_vp, _i, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp],
     "tn_logmel_power_f32": [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
     "tn_logmel_finish_f32": [_vp, _vp, _vp, _i, _i64, _i, _vp],
-    "tn_feat_stack_f32": [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp],
+    "tn_feat_stack_f32": [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp],
     "tn_embed_add_bf16": [_vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _i64, _vp],
     "tn_cast_f32_bf16": [_vp, _vp, _i64, _vp],
 }
@@ -72,9 +72,27 @@ def load(path: str | None = None) -> ctypes.CDLL:
     return lib
 
 
+# kernels launched per entry point (for bench.py's `gpu_launches` claim)
+_LAUNCHES = {"tn_attn_prep": 2, "tn_attn_bwd_bf16": 3, "tn_logmel_power_f32": 2}
+launch_count = 0
+_hooks = []   # callables(name, phase) with phase in {"pre", "post"}; bench.py uses them to time kernel classes
+
+
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point; non-zero -> TouchNetB200Error(tn_last_error())."""
+    global launch_count
     lib = load()
+    launch_count += _LAUNCHES.get(name, 1)
+    if _hooks:
+        for h in _hooks:
+            h(name, "pre", args)
+        rc = getattr(lib, name)(*args)
+        for h in _hooks:
+            h(name, "post", args)
+        if rc != 0:
+            msg = lib.tn_last_error()
+            raise TouchNetB200Error(f"{name} failed (rc={rc}): {msg.decode() if msg else '?'}")
+        return
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.tn_last_error()

@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(256) feat_stack_kernel(const float* __restrict
                                                          const int64_t* __restrict__ frame_offsets,
                                                          const int64_t* __restrict__ out_offsets, int n_utts,
                                                          int64_t total_out_rows, int n_mels, int stack, int stride,
-                                                         int normalize, float* __restrict__ out) {
+                                                         int normalize, float* __restrict__ out,
+                                                         const int64_t* __restrict__ dst_row0, int64_t out_ld) {
   const int64_t row = int64_t(blockIdx.x) * 8 + warp_id();
   if (row >= total_out_rows) return;
   const uint32_t lane = lane_id();
@@ -229,7 +230,8 @@ __global__ void __launch_bounds__(256) feat_stack_kernel(const float* __restrict
   const int64_t T = frame_offsets[u + 1] - f0;
   const int left = (stack - 1) / 2;
   const int width = stack * n_mels;
-  float* dst = out + row * width;
+  // packed output (row-major, back to back) or scattered into a [B*T, out_ld] batch buffer at dst_row0[u] + i
+  float* dst = dst_row0 ? out + (dst_row0[u] + i) * out_ld : out + row * width;
   float sum = 0.f;
   for (int c = lane; c < width; c += 32) {
     const int s = c / n_mels, m = c - s * n_mels;
@@ -325,7 +327,7 @@ extern "C" int tn_logmel_finish_f32(float* feats, const int64_t* frame_offsets, 
 
 extern "C" int tn_feat_stack_f32(const float* feats, const int64_t* frame_offsets, const int64_t* out_offsets, int n_utts,
                                  int64_t total_out_rows, int n_mels, int stack, int stride, int normalize, float* out,
-                                 tn_stream_t stream_) {
+                                 const int64_t* dst_row0, int64_t out_ld, tn_stream_t stream_) {
   clear_error();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TN_REQUIRE(feats && frame_offsets && out_offsets && out, "tn_feat_stack_f32: null pointer");
@@ -333,7 +335,8 @@ extern "C" int tn_feat_stack_f32(const float* feats, const int64_t* frame_offset
   if (total_out_rows == 0) return TN_OK;
   feat_stack_kernel<<<unsigned((total_out_rows + 7) / 8), 256, 0, stream>>>(feats, frame_offsets, out_offsets, n_utts,
                                                                            total_out_rows, n_mels, stack, stride,
-                                                                           normalize, out);
+                                                                           normalize, out, dst_row0,
+                                                                           out_ld > 0 ? out_ld : int64_t(stack) * n_mels);
   TN_CHECK_CUDA(cudaGetLastError());
   return TN_OK;
 }

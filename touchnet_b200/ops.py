@@ -49,27 +49,31 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
+_BF16_CACHE: dict[int, tuple[int, torch.Tensor]] = {}
+
+
 def bf16_weight(w: torch.Tensor) -> torch.Tensor:
-    """bf16 view of a parameter: the tensor itself if already bf16, else a cached cast keyed on the version counter."""
-    w = w.detach()
+    """bf16 working copy of a parameter: the tensor itself if already bf16 (FSDP2 mixed precision hands the modules
+    bf16 unsharded parameters), else a cached cast of the fp32 master keyed on (storage address, version counter) so
+    that forward and backward of one step share a single cast."""
     if w.dtype == BF16:
+        w = w.detach()
         return w if w.is_contiguous() else w.contiguous()
-    cache = getattr(w, "_tn_bf16", None)
-    if cache is not None and cache[0] == w._version and cache[1].shape == w.shape and cache[1].device == w.device:
-        return cache[1]
-    out = cast_bf16(w, cache[1] if cache is not None and cache[1].shape == w.shape and cache[1].device == w.device else None)
-    w._tn_bf16 = (w._version, out)
+    key, ver = w.data_ptr(), w._version
+    ent = _BF16_CACHE.get(key)
+    if ent is not None and ent[0] == ver and ent[1].shape == w.shape and ent[1].device == w.device:
+        return ent[1]
+    reuse = ent[1] if ent is not None and ent[1].shape == w.shape and ent[1].device == w.device else None
+    out = cast_bf16(w.detach(), reuse)
+    _BF16_CACHE[key] = (ver, out)
     return out
 
 
-def drop_bf16_cache(module: torch.nn.Module) -> None:
-    """Forget cached bf16 copies (bench.py calls this every step so the cast is inside the timed region)."""
-    for p in module.parameters():
-        if hasattr(p, "_tn_bf16"):
-            p._tn_bf16 = (-1, p._tn_bf16[1])
-        d = p.detach()
-        if hasattr(d, "_tn_bf16"):
-            d._tn_bf16 = (-1, d._tn_bf16[1])
+def invalidate_bf16_cache() -> None:
+    """Force a fresh fp32->bf16 cast on next use (bench.py calls this every step: the cast is part of the step, as the
+    all-gather-time cast is under FSDP2)."""
+    for k, (ver, t) in list(_BF16_CACHE.items()):
+        _BF16_CACHE[k] = (-1, t)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -320,6 +324,23 @@ class PackedAttentionFn(torch.autograd.Function):
         rope_apply_(dq, cos, sin, ctx.H, 128, inverse=True)
         rope_apply_(dk, cos, sin, ctx.KV, 128, inverse=True)
         return dq, dk, dv, None, None, None, None, None, None
+
+
+class AttentionFn(torch.autograd.Function):
+    """Document-masked attention on already-rotated q/k (the HF attention-interface seam hands RoPE'd tensors)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, plan, H, KV, scale):
+        o, lse = attn_fwd(q, k, v, plan, H, KV, scale)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.plan, ctx.H, ctx.KV, ctx.scale = plan, H, KV, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        dq, dk, dv = attn_bwd(q, k, v, o, do, lse, ctx.plan, ctx.H, ctx.KV, ctx.scale)
+        return dq, dk, dv, None, None, None, None
 
 
 class SwiGLUFn(torch.autograd.Function):

@@ -1,0 +1,156 @@
+"""Plugin registration: how the B200 modules enter the reference's train loop with no edit to touchnet/bin/train.py.
+
+Two seams:
+
+1. Outer plugin API - `TrainSpec` (ref: touchnet/utils/train_spec.py:25-62).  `register()` clones the reference's own
+   "llama" / "touch_audio" specs (ref: touchnet/__init__.py:35-117) and swaps `model_cls` for the B200 modules under the
+   names "llama_b200" / "touch_audio_b200"; every other callable (parallelize_fn, dataloader, optimizer, loss, flops ...)
+   stays the reference's.  `--training_model_name touch_audio_b200` then selects it (ref: touchnet/bin/train.py:119).
+
+2. Inner operator API - HF's attention-interface registry
+   (`ALL_ATTENTION_FUNCTIONS[config._attn_implementation]`, hf: models/llama/modeling_llama.py:272-286;
+   FlexAttention entry hf: integrations/flex_attention.py:262-364).  `register_hf_attention()` installs
+   "touchnet_b200": same signature and return convention as `flex_attention_forward`, document ids supplied either as
+   the `[B,T]` integer `attention_mask` itself or through `packed_document_ids(...)`.
+"""
+from __future__ import annotations
+
+import contextlib
+import dataclasses
+import threading
+from dataclasses import dataclass
+from typing import Any, Callable, Optional
+
+import torch
+
+from . import modeling, ops
+
+_tls = threading.local()
+
+
+@dataclass
+class TrainSpec:
+    """Field-for-field mirror of ref: touchnet/utils/train_spec.py:25-44 (used when the reference is not importable)."""
+    name: str
+    model_cls: Any
+    config_cls: Any
+    parallelize_fn: Optional[Callable] = None
+    pipelining_fn: Optional[Callable] = None
+    build_optimizers_fn: Optional[Callable] = None
+    build_lr_schedulers_fn: Optional[Callable] = None
+    build_dataloader_fn: Optional[Callable] = None
+    build_tokenizer_fn: Optional[Callable] = None
+    loss_fn: Optional[Callable] = None
+    acc_fn: Optional[Callable] = None
+    additional_pre_init_fn: Optional[Callable] = None
+    additional_post_init_fn: Optional[Callable] = None
+    get_num_flop_per_token_fn: Optional[Callable] = None
+    get_num_params_fn: Optional[Callable] = None
+    build_metrics_processor_fn: Optional[Callable] = None
+
+
+_local_specs: dict[str, TrainSpec] = {}
+
+
+def get_num_flop_per_token(num_params: int, model_config, seq_len: int) -> int:
+    """ref: touchnet/models/llama/__init__.py:39-54 (dense-attention convention, no recompute credit)."""
+    l, h = model_config.num_hidden_layers, model_config.num_attention_heads
+    q = model_config.hidden_size // model_config.num_attention_heads
+    return 6 * num_params + 12 * l * h * q * seq_len
+
+
+def get_num_params(model: torch.nn.Module, exclude_embedding: bool = False) -> int:
+    """ref: touchnet/models/llama/__init__.py:57-67."""
+    n = sum(p.numel() for p in model.parameters())
+    if exclude_embedding:
+        sub = getattr(model, getattr(model, "base_model_prefix", "model"))
+        sub = getattr(sub, "model", sub) if not any(isinstance(m, torch.nn.Embedding) for m in sub.children()) else sub
+        n -= sum(sum(p.numel() for p in m.parameters()) for m in sub.children() if isinstance(m, torch.nn.Embedding))
+    return n
+
+
+def register(touchnet_pkg=None) -> list[str]:
+    """Register "llama_b200" and "touch_audio_b200".  With the reference importable its registry is used (and its own
+    specs cloned); otherwise the specs land in this module's registry with the reference-independent callables."""
+    names = []
+    try:
+        if touchnet_pkg is None:
+            import touchnet as touchnet_pkg  # type: ignore
+        from touchnet.utils.train_spec import get_train_spec, register_train_spec  # type: ignore
+        for base, cls in (("llama", modeling.B200LlamaForCausalLM), ("touch_audio", modeling.B200TouchAudioForCausalLM)):
+            spec = dataclasses.replace(get_train_spec(base), name=base + "_b200", model_cls=cls)
+            try:
+                register_train_spec(spec)
+            except ValueError:
+                pass  # already registered
+            names.append(spec.name)
+        return names
+    except Exception:
+        for base, cls in (("llama", modeling.B200LlamaForCausalLM), ("touch_audio", modeling.B200TouchAudioForCausalLM)):
+            spec = TrainSpec(name=base + "_b200", model_cls=cls, config_cls=None,
+                             get_num_flop_per_token_fn=get_num_flop_per_token, get_num_params_fn=get_num_params)
+            _local_specs[spec.name] = spec
+            names.append(spec.name)
+        return names
+
+
+def get_train_spec(name: str) -> TrainSpec:
+    if name not in _local_specs:
+        raise ValueError(f"Model {name} is not registered.")
+    return _local_specs[name]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# HF attention-interface seam
+# ---------------------------------------------------------------------------------------------------------------
+@contextlib.contextmanager
+def packed_document_ids(doc_ids: torch.Tensor):
+    """Make the `[B,T]` document-id tensor of the current packed batch visible to `hf_attention_forward` when the
+    caller's mask plumbing has already turned `attention_mask` into something else (BlockMask / 4-D mask)."""
+    prev = getattr(_tls, "plan", None)
+    _tls.plan = ops.AttnPlan(doc_ids)
+    try:
+        yield
+    finally:
+        _tls.plan = prev
+
+
+def hf_attention_forward(module, query, key, value, attention_mask=None, dropout: float = 0.0, scaling=None,
+                         **kwargs):
+    """Drop-in for `flex_attention_forward(module, query [B,H,T,hd], key [B,KV,T,hd], value, attention_mask, ...)`
+    (hf: integrations/flex_attention.py:262-364): returns (attn_output [B,T,H,hd], None)."""
+    B, H, T, hd = query.shape
+    KV = key.shape[1]
+    if hd != 128:
+        raise ops._lib.TouchNetB200Error(f"touchnet_b200 attention needs head_dim 128, got {hd}")
+    if dropout:
+        raise ops._lib.TouchNetB200Error("attention dropout is not supported (0.0 in every reference config)")
+    if isinstance(attention_mask, torch.Tensor) and attention_mask.dim() == 2 and not attention_mask.is_floating_point():
+        plan = ops.AttnPlan(attention_mask)
+    else:
+        plan = getattr(_tls, "plan", None)
+        if plan is None:
+            plan = ops.AttnPlan(torch.ones((B, T), dtype=torch.int32, device=query.device))   # plain causal
+    q2 = query.transpose(1, 2).reshape(B * T, H * hd)      # a view when q is the usual transposed projection output
+    k2 = key.transpose(1, 2).reshape(B * T, KV * hd)
+    v2 = value.transpose(1, 2).reshape(B * T, KV * hd)
+    dt = query.dtype
+    if dt != torch.bfloat16:
+        q2, k2, v2 = q2.bfloat16(), k2.bfloat16(), v2.bfloat16()
+    scale = float(scaling) if scaling is not None else hd ** -0.5
+    o = ops.AttentionFn.apply(q2, k2, v2, plan, H, KV, scale)
+    return o.view(B, T, H, hd).to(dt), None
+
+
+def register_hf_attention(name: str = "touchnet_b200") -> bool:
+    """`"attn_implementation": "touchnet_b200"` in the model JSON then selects the kernel (cf. "flex_attention" at
+    ref: examples/text/pretrain/fineweb-edu/config/Llama-3_2-1B.json:7)."""
+    try:
+        from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+    except Exception:
+        return False
+    try:
+        ALL_ATTENTION_FUNCTIONS.register(name, hf_attention_forward)
+    except AttributeError:
+        ALL_ATTENTION_FUNCTIONS[name] = hf_attention_forward
+    return True

@@ -97,6 +97,11 @@ def make_host_batch(seed: int, B: int, T: int, vocab: int):
     return host, meta
 
 
+def dist_util_seed(base, rank):
+    from touchnet_b200 import dist_util
+    return dist_util.rank_seed(base, rank)
+
+
 def to_device(host: dict, dev) -> dict:
     return {k: v.to(dev, non_blocking=True) for k, v in host.items()}
 
@@ -352,7 +357,7 @@ def main():
         fully_shard(model, mesh=mesh, mp_policy=mp, reshard_after_forward=True)
     model.train()
 
-    host, meta = make_host_batch(2025 + rank, B, T, cfg.text_config.vocab_size)
+    host, meta = make_host_batch(dist_util_seed(2025, rank), B, T, cfg.text_config.vocab_size)
     resident = to_device(host, dev)
     torch.cuda.synchronize()
 
@@ -387,12 +392,10 @@ def main():
     launches = _lib.launch_count - launches0
     ms = e0.elapsed_time(e1)
     gemm_ms, gemm_flops, gemm_n = gt.summary()
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    from touchnet_b200 import dist_util
+    ms = dist_util.max_over_ranks(ms, dev)
     tokens_per_step = B * T * world
-    value = tokens_per_step * args.steps / (ms * 1e-3)
+    value = dist_util.whole_job_tokens_per_s(B * T, args.steps, world, ms)
     final_loss = float(loss.item())
 
     # ---------------- end-to-end arm: pinned host inputs, H2D inside, loss read back every step ----------------
@@ -409,10 +412,7 @@ def main():
         t1.record()
         barrier()
         ms2 = t0.elapsed_time(t1)
-        if dist is not None:
-            t = torch.tensor([ms2], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms2 = float(t.item())
+        ms2 = dist_util.max_over_ranks(ms2, dev)
         e2e = {"value": tokens_per_step * args.steps / (ms2 * 1e-3), "unit": "tokens/s",
                "h2d_bytes_per_step": h2d_bytes(host), "d2h_bytes_per_step": 4}
 

@@ -21,7 +21,14 @@ CASES = {
     "tn_odd":     (264, 1040, 200, 1, 1, 1, 0, 0),
     "swiglu":     (512, 1024, 512, 0, 0, 0, 0, 1),
     "swiglu_odd": (200, 264, 1040, 0, 0, 0, 0, 1),
+    "pair_tail":  (300, 520, 1040, 0, 0, 0, 1, 0),
+    "pair_tail_nn": (300, 520, 1040, 0, 1, 0, 0, 0),
+    "pair_tail_tn": (520, 1040, 300, 1, 1, 1, 1, 0),
+    "swiglu_tail": (300, 392, 1040, 0, 0, 0, 0, 1),
     "perf_qo":    (8192, 4096, 4096, 0, 0, 0, 0, 0),
+    "perf_kv":    (8192, 1024, 4096, 0, 0, 0, 0, 0),
+    "perf_lmhead": (8192, 128256, 4096, 0, 0, 0, 0, 0),
+    "perf_wgrad_qo": (4096, 4096, 8192, 1, 1, 1, 0, 0),
     "perf_down":  (8192, 4096, 14336, 0, 0, 0, 1, 0),
     "perf_dgrad": (8192, 4096, 14336, 0, 1, 0, 0, 0),
     "perf_wgrad": (14336, 4096, 8192, 1, 1, 1, 0, 0),
@@ -102,9 +109,19 @@ def run_case(name):
 
 def main():
     ap = argparse.ArgumentParser(); ap.add_argument("--case", default=None); ap.add_argument("--only", default=None)
+    ap.add_argument("--inproc", action="store_true", help="all cases in this process (one torch import)")
     a = ap.parse_args()
     if a.case:
         run_case(a.case); return
+    if a.inproc:
+        import traceback
+        for n in CASES:
+            if a.only is None or a.only in n:
+                try:
+                    run_case(n)
+                except Exception as e:
+                    print("RESULT " + json.dumps({"case": n, "ok": False, "exc": repr(e)[:300]}), flush=True)
+        print("DONE", flush=True); return
     os.environ.setdefault("TN_DEV_PARTIAL", "1")
     names = [n for n in CASES if (a.only is None or a.only in n)]
     nfail = 0

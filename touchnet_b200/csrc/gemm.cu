@@ -13,6 +13,7 @@
 // Operands may be K-major or MN-major (descriptor bits), so forward, dgrad and wgrad all run on the
 // tensors where they lie: no transposes, no copies.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/touchnet_b200.h"
 #include "common.cuh"
@@ -334,6 +335,22 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 }  // namespace tn
 
+namespace tn {
+int gemm_pair_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
+                       int d_f32, const void* R, int64_t ldr, int M, int N, int K, cudaStream_t stream);
+int gemm_pair_swiglu_dispatch(const void* X, int64_t ldx, const void* Wg, const void* Wu, int64_t ldw, void* G, void* U,
+                              void* H, int64_t ldh, int M, int N, int K, cudaStream_t stream);
+// TN_GEMM_PAIR=0 forces the single-CTA kernels (A/B measurements); default: CTA pairs whenever the tile fits
+static bool use_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TN_GEMM_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+}  // namespace tn
+
 using namespace tn;
 
 extern "C" int tn_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D,
@@ -348,6 +365,9 @@ extern "C" int tn_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B,
   TN_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0 && (!R || (reinterpret_cast<uintptr_t>(R) & 15) == 0),
              "tn_gemm_bf16: D/R must be 16 B aligned");
   TN_REQUIRE(!(a_mn && !b_mn), "tn_gemm_bf16: (a_mn=1, b_mn=0) layout is not instantiated");
+
+  if (use_pair() && M >= 256 && N >= 256)
+    return gemm_pair_dispatch(A, lda, a_mn, B, ldb, b_mn, D, ldd, d_f32, R, ldr, M, N, K, stream);
 
   // small-N problems use the narrower tile so that the persistent grid still fills 148 SMs
   const bool narrow = (int64_t((M + BM - 1) / BM) * ((N + 255) / 256) < 148) || (N <= 128);
@@ -388,6 +408,8 @@ extern "C" int tn_gemm_swiglu_bf16(const void* X, int64_t ldx, const void* Wg, c
   TN_REQUIRE((reinterpret_cast<uintptr_t>(H) & 15) == 0 && (!G || (reinterpret_cast<uintptr_t>(G) & 15) == 0) &&
                  (!U || (reinterpret_cast<uintptr_t>(U) & 15) == 0),
              "tn_gemm_swiglu_bf16: outputs must be 16 B aligned");
+  if (use_pair() && M >= 256 && N >= 128 && G && U)
+    return gemm_pair_swiglu_dispatch(X, ldx, Wg, Wu, ldw, G, U, H, ldh, M, N, K, stream);
   constexpr int BN = 256;  // 128 gate + 128 up accumulator columns
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;

@@ -1,0 +1,380 @@
+// touchnet_b200 :: CTA-pair tcgen05 GEMM (cta_group::2).  256 x 256 x 64 tiles computed by two CTAs of one cluster:
+// each CTA stages 128 rows of A and 128 rows of B per k-block (32 KB instead of 48 KB for the same MMA work), the
+// leader CTA issues one tcgen05.mma.cta_group::2 (M=256) that reads B from both CTAs' shared memory, each CTA's TMEM
+// holds its 128 accumulator rows (2 x 256 columns, double buffered), and the epilogue goes TMEM -> registers ->
+// 128B-swizzled smem staging -> TMA store (fully coalesced, clipped at the tensor edges by the hardware).
+//
+// Same call sites as gemm.cu (F.linear forward / dgrad / wgrad of hf:models/llama/modeling_llama.py:251-289,
+// 182-184); tn_gemm_bf16 / tn_gemm_swiglu_bf16 dispatch here for M,N >= 256.
+#include "../../include/touchnet_b200.h"
+#include "common.cuh"
+#include "host.h"
+
+namespace tn {
+
+constexpr int P_BM = 128;        // rows of A (and of D) per CTA
+constexpr int P_BN = 256;        // D columns per cluster tile; each CTA stages P_BN/2 rows of B
+constexpr int P_BK = 64;
+constexpr int P_THREADS = 256;
+constexpr int P_GROUP = 8;
+constexpr int P_A_BYTES = P_BM * P_BK * 2;        // 16 KB
+constexpr int P_B_BYTES = (P_BN / 2) * P_BK * 2;  // 16 KB
+constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
+constexpr int P_STG_BYTES = 128 * 128;            // one staging buffer: 128 rows x 128 B
+
+template <int EPI>
+struct PairCfg {
+  static constexpr int STAGES = (EPI == 1) ? 5 : 6;
+  static constexpr int NSTG = (EPI == 1) ? 3 : 2;   // swiglu: G, U, H buffers; else double buffer
+  static constexpr int STG_OFF = STAGES * P_STAGE_BYTES;
+  static constexpr int BAR_OFF = STG_OFF + NSTG * P_STG_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+};
+
+struct PairParams {
+  int M, N, K;
+  int num_m, num_n, num_k;   // num_m in units of 256 rows
+  const void* R;
+  int64_t ldr;
+};
+
+__device__ __forceinline__ void pair_decode_tile(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+  const int per_group = P_GROUP * num_n;
+  const int g = tile / per_group;
+  const int first_m = g * P_GROUP;
+  const int gsize = min(num_m - first_m, P_GROUP);
+  const int r = tile - g * per_group;
+  m_blk = first_m + (r % gsize);
+  n_blk = r / gsize;
+}
+
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// EPI: 0 = bf16 D = acc (+R);  1 = SwiGLU (cols [0,128) gate, [128,256) up -> G,U,H);  2 = fp32 D = acc (+R)
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD,
+                 const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3, const PairParams p) {
+  using Cfg = PairCfg<EPI>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * P_A_BYTES;
+  uint8_t* sStg = smem + Cfg::STG_OFF;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmD);
+    if (EPI == 1) { tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmD2); tma_prefetch_desc(&tmD3); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }  // 4 warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // peer's barriers are initialised before anything remote touches them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = p.num_m * p.num_n;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; transaction bytes counted on the leader's barrier) ============
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int m_blk, n_blk;
+        pair_decode_tile(tile, p.num_m, p.num_n, m_blk, n_blk);
+        const int m0 = m_blk * 256 + int(rank) * P_BM;
+        const int n0 = (EPI == 1) ? n_blk * 128 : n_blk * P_BN + int(rank) * (P_BN / 2);
+        for (int kb = 0; kb < p.num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * P_A_BYTES;
+          uint8_t* b_dst = sB + stage * P_B_BYTES;
+          const int k0 = kb * P_BK;
+          if (!A_MN) {
+            tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], k0, m0);
+          } else {
+            tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], m0, k0);
+            tma_load_2d_pair(a_dst + 8192, &tmA, &full_bar[stage], m0 + 64, k0);
+          }
+          if (EPI == 1) {
+            tma_load_2d_pair(b_dst, rank == 0 ? &tmB : &tmB2, &full_bar[stage], k0, n0);  // CTA0: gate rows, CTA1: up rows
+          } else if (!B_MN) {
+            tma_load_2d_pair(b_dst, &tmB, &full_bar[stage], k0, n0);
+          } else {
+            tma_load_2d_pair(b_dst, &tmB, &full_bar[stage], n0, k0);
+            tma_load_2d_pair(b_dst + 8192, &tmB, &full_bar[stage], n0 + 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, P_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * P_BN);
+        for (int kb = 0; kb < p.num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * P_A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * P_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < P_BK / 16; ++k) {
+            const uint64_t da = A_MN ? make_sdesc_sw128(a_addr + k * 2048, 8192, 1024)
+                                     : make_sdesc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t db = B_MN ? make_sdesc_sw128(b_addr + k * 2048, 8192, 1024)
+                                     : make_sdesc_sw128(b_addr + k * 32, 0, 1024);
+            umma_ss_pair(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 0b11);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[acc], 0b11);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): TMEM -> regs -> swizzled smem -> TMA store =====================
+    const uint32_t quad = warp & 3u;
+    const uint32_t r = quad * 32 + lane;         // row inside this CTA's 128-row slab == TMEM lane
+    const int etid = int(threadIdx.x) - 128;     // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t n_issued = 0;                       // staging rounds issued so far (buffer ring position)
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int m_blk, n_blk;
+      pair_decode_tile(tile, p.num_m, p.num_n, m_blk, n_blk);
+      const int row0 = m_blk * 256 + int(rank) * P_BM;
+      const int row = row0 + int(r);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + uint32_t(acc * P_BN) + ((quad * 32u) << 16);
+
+      if (EPI == 1) {
+        const int n0 = n_blk * 128;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 64) {
+          if (n_issued > 0) {
+            if (etid == 0) tma_store_wait_read<0>();
+            named_bar(2, 128);
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t g[32], u[32];
+            tmem_ld32(t_row + c + half * 32, g);
+            tmem_ld32(t_row + 128 + c + half * 32, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t pg[4], pu[4], ph[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = q * 8 + j * 2;
+                const float g0 = bf16_round(__uint_as_float(g[i])), g1 = bf16_round(__uint_as_float(g[i + 1]));
+                const float u0 = bf16_round(__uint_as_float(u[i])), u1 = bf16_round(__uint_as_float(u[i + 1]));
+                const float s0 = bf16_round(g0 / (1.f + __expf(-g0))), s1 = bf16_round(g1 / (1.f + __expf(-g1)));
+                pg[j] = pack_bf16x2(g0, g1);
+                pu[j] = pack_bf16x2(u0, u1);
+                ph[j] = pack_bf16x2(s0 * u0, s1 * u1);
+              }
+              const uint32_t off = r * 128u + (((uint32_t(half * 4 + q)) ^ (r & 7u)) << 4);
+              *reinterpret_cast<uint4*>(sStg + off) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+              *reinterpret_cast<uint4*>(sStg + P_STG_BYTES + off) = make_uint4(pu[0], pu[1], pu[2], pu[3]);
+              *reinterpret_cast<uint4*>(sStg + 2 * P_STG_BYTES + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar(2, 128);
+          if (etid == 0) {
+            tma_store_2d(&tmD2, sStg, n0 + c, row0);                    // G
+            tma_store_2d(&tmD3, sStg + P_STG_BYTES, n0 + c, row0);      // U
+            tma_store_2d(&tmD, sStg + 2 * P_STG_BYTES, n0 + c, row0);   // H
+            tma_store_commit();
+          }
+          ++n_issued;
+        }
+      } else {
+        constexpr int CW = (EPI == 2) ? 32 : 64;   // columns per staging round (128 B per row)
+        const int n0 = n_blk * P_BN;
+#pragma unroll 1
+        for (int c = 0; c < P_BN; c += CW) {
+          uint8_t* stg = sStg + (n_issued & 1u) * P_STG_BYTES;
+          if (n_issued >= 2) {
+            if (etid == 0) tma_store_wait_read<1>();   // the store that last read this buffer has drained it
+            named_bar(2, 128);
+          }
+          const int col = n0 + c;
+          if (EPI == 2) {
+            uint32_t v[32];
+            tmem_ld32(t_row + c, v);
+            tmem_ld_wait();
+            if (p.R && row < p.M && col < p.N) {
+              const float* rptr = reinterpret_cast<const float*>(p.R) + int64_t(row) * p.ldr + col;
+              if (col + 32 <= p.N) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 r4 = reinterpret_cast<const float4*>(rptr)[q];
+                  v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + r4.x);
+                  v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + r4.y);
+                  v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + r4.z);
+                  v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + r4.w);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col + i < p.N) v[i] = __float_as_uint(__uint_as_float(v[i]) + rptr[i]);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(stg + r * 128u + ((uint32_t(q) ^ (r & 7u)) << 4)) =
+                  make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t v[32];
+              tmem_ld32(t_row + c + half * 32, v);
+              tmem_ld_wait();
+              const int hcol = col + half * 32;
+              const bool has_r = p.R && row < p.M && hcol < p.N;
+              const bf16* rptr = has_r ? reinterpret_cast<const bf16*>(p.R) + int64_t(row) * p.ldr + hcol : nullptr;
+              const bool vec_r = has_r && (hcol + 32 <= p.N);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 r4 = make_uint4(0, 0, 0, 0);
+                if (vec_r) r4 = reinterpret_cast<const uint4*>(rptr)[q];
+                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float lo = __uint_as_float(v[8 * q + 2 * j]), hi = __uint_as_float(v[8 * q + 2 * j + 1]);
+                  if (vec_r) {
+                    lo = bf16_round(lo) + bf16lo(rw[j]);
+                    hi = bf16_round(hi) + bf16hi(rw[j]);
+                  } else if (has_r) {
+                    const int i0 = 8 * q + 2 * j;
+                    if (hcol + i0 < p.N) lo = bf16_round(lo) + __bfloat162float(rptr[i0]);
+                    if (hcol + i0 + 1 < p.N) hi = bf16_round(hi) + __bfloat162float(rptr[i0 + 1]);
+                  }
+                  w[j] = pack_bf16x2(lo, hi);
+                }
+                *reinterpret_cast<uint4*>(stg + r * 128u + ((uint32_t(half * 4 + q) ^ (r & 7u)) << 4)) =
+                    make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar(2, 128);
+          if (etid == 0) {
+            tma_store_2d(&tmD, stg, col, row0);
+            tma_store_commit();
+          }
+          ++n_issued;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (etid == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // nobody leaves while the peer may still read our smem / arrive on our barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const CUtensorMap& tmD,
+                       const CUtensorMap& tmD2, const CUtensorMap& tmD3, const PairParams& p, cudaStream_t stream) {
+  using Cfg = PairCfg<EPI>;
+  auto kern = gemm_pair_kernel<A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    TN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = p.num_m * p.num_n;
+  const int max_clusters = sm_count() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  kern<<<clusters * 2, P_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB2, tmD, tmD2, tmD3, p);
+  TN_CHECK_CUDA(cudaGetLastError());
+  return TN_OK;
+}
+
+// ---- entry points used by gemm.cu's dispatcher ----
+int gemm_pair_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* D, int64_t ldd,
+                       int d_f32, const void* R, int64_t ldr, int M, int N, int K, cudaStream_t stream) {
+  PairParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
+  p.R = R; p.ldr = ldr;
+  CUtensorMap tmA, tmB, tmD;
+  int rc;
+  if (!a_mn) rc = encode_tmap_2d(&tmA, A, 2, uint64_t(K), uint64_t(M), uint64_t(lda) * 2, 64, P_BM, true);
+  else       rc = encode_tmap_2d(&tmA, A, 2, uint64_t(M), uint64_t(K), uint64_t(lda) * 2, 64, 64, true);
+  if (rc) return rc;
+  if (!b_mn) rc = encode_tmap_2d(&tmB, B, 2, uint64_t(K), uint64_t(N), uint64_t(ldb) * 2, 64, P_BN / 2, true);
+  else       rc = encode_tmap_2d(&tmB, B, 2, uint64_t(N), uint64_t(K), uint64_t(ldb) * 2, 64, 64, true);
+  if (rc) return rc;
+  if (d_f32) rc = encode_tmap_2d(&tmD, D, 4, uint64_t(N), uint64_t(M), uint64_t(ldd) * 4, 32, 128, true);
+  else       rc = encode_tmap_2d(&tmD, D, 2, uint64_t(N), uint64_t(M), uint64_t(ldd) * 2, 64, 128, true);
+  if (rc) return rc;
+#define TN_PAIR(AMN_, BMN_)                                                                   \
+  (d_f32 ? launch_pair<AMN_, BMN_, 2>(tmA, tmB, tmB, tmD, tmD, tmD, p, stream)                \
+         : launch_pair<AMN_, BMN_, 0>(tmA, tmB, tmB, tmD, tmD, tmD, p, stream))
+  if (!a_mn && !b_mn) return TN_PAIR(false, false);
+  if (!a_mn && b_mn) return TN_PAIR(false, true);
+  return TN_PAIR(true, true);
+#undef TN_PAIR
+}
+
+int gemm_pair_swiglu_dispatch(const void* X, int64_t ldx, const void* Wg, const void* Wu, int64_t ldw, void* G, void* U,
+                              void* H, int64_t ldh, int M, int N, int K, cudaStream_t stream) {
+  PairParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.num_m = (M + 255) / 256; p.num_n = (N + 127) / 128; p.num_k = (K + P_BK - 1) / P_BK;
+  CUtensorMap tmA, tmG, tmU, tmDG, tmDU, tmDH;
+  int rc;
+  if ((rc = encode_tmap_2d(&tmA, X, 2, uint64_t(K), uint64_t(M), uint64_t(ldx) * 2, 64, P_BM, true))) return rc;
+  if ((rc = encode_tmap_2d(&tmG, Wg, 2, uint64_t(K), uint64_t(N), uint64_t(ldw) * 2, 64, 128, true))) return rc;
+  if ((rc = encode_tmap_2d(&tmU, Wu, 2, uint64_t(K), uint64_t(N), uint64_t(ldw) * 2, 64, 128, true))) return rc;
+  if ((rc = encode_tmap_2d(&tmDG, G, 2, uint64_t(N), uint64_t(M), uint64_t(ldh) * 2, 64, 128, true))) return rc;
+  if ((rc = encode_tmap_2d(&tmDU, U, 2, uint64_t(N), uint64_t(M), uint64_t(ldh) * 2, 64, 128, true))) return rc;
+  if ((rc = encode_tmap_2d(&tmDH, H, 2, uint64_t(N), uint64_t(M), uint64_t(ldh) * 2, 64, 128, true))) return rc;
+  return launch_pair<false, false, 1>(tmA, tmG, tmU, tmDH, tmDG, tmDU, p, stream);
+}
+
+}  // namespace tn

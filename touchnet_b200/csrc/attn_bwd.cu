@@ -24,12 +24,13 @@ constexpr int RES_CHUNK = RES_BYTES / 2;
 constexpr int STR_BYTES = SUB * ATT_HD * 2;           // 16 KB streamed tile (2 chunks of 8 KB)
 constexpr int STR_CHUNK = STR_BYTES / 2;
 constexpr int PT_BYTES = ATT_BLK * SUB * 2;           // 16 KB  [128 rows x 128 B]
+constexpr int NST = 3;                                // streamed-tile ring depth (TMA latency hidden behind 2 iterations)
 
 struct BwdSmem {
   static constexpr int R1 = 0;
   static constexpr int R2 = R1 + RES_BYTES;
-  static constexpr int T = R2 + RES_BYTES;                  // 2 stages x (T1, T2)
-  static constexpr int PT = T + 2 * 2 * STR_BYTES;
+  static constexpr int T = R2 + RES_BYTES;                  // NST stages x (T1, T2)
+  static constexpr int PT = T + NST * 2 * STR_BYTES;
   static constexpr int DST = PT + PT_BYTES;
   static constexpr int COL = DST + PT_BYTES;                // 2 x {lse2[64], delta[64], doc[64]}
   static constexpr int BARS = COL + 2 * 3 * SUB * 4;
@@ -93,12 +94,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   float* sCol = reinterpret_cast<float*>(smem + BwdSmem::COL);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BARS);
   uint64_t* r_full = bars + 0;
-  uint64_t* t_full = bars + 1;    // [2]
-  uint64_t* t_empty = bars + 3;   // [2]
-  uint64_t* xy_full = bars + 5;   // [2]
-  uint64_t* pds_full = bars + 7;
-  uint64_t* acc_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* t_full = bars + 1;    // [NST]
+  uint64_t* t_empty = bars + 5;   // [NST]
+  uint64_t* xy_full = bars + 9;   // [2]
+  uint64_t* pds_full = bars + 11;
+  uint64_t* acc_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const uint32_t warp = warp_id(), lane = lane_id();
   const int blk = DKDV ? int(blockIdx.x) : p.nblk - 1 - int(blockIdx.x);
@@ -132,9 +133,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     mbar_init(r_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 1); mbar_init(&xy_full[s], 1);
-    }
+    for (int s = 0; s < NST; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) mbar_init(&xy_full[s], 1);
     mbar_init(pds_full, 128);
     mbar_init(acc_done, 1);
     fence_barrier_init();
@@ -159,8 +159,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       tma_load_3d(sR2, &tmR2, r_full, hy * ATT_HD, r0, b);
       tma_load_3d(sR2 + RES_CHUNK, &tmR2, r_full, hy * ATT_HD + 64, r0, b);
       for (int t = 0; t < n; ++t) {
-        const int s = t & 1;
-        mbar_wait(&t_empty[s], ((t >> 1) & 1) ^ 1);
+        const int s = t % NST;
+        mbar_wait(&t_empty[s], ((t / NST) & 1) ^ 1);
         mbar_arrive_expect_tx(&t_full[s], 2 * STR_BYTES);
         uint8_t* d1 = sT + s * 2 * STR_BYTES;
         uint8_t* d2 = d1 + STR_BYTES;
@@ -179,11 +179,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, ATT_HD, 0, 1);
       const uint32_t r1 = smem_u32(sR1), r2 = smem_u32(sR2), pt = smem_u32(sPT), dst = smem_u32(sDST);
       auto issue_xy = [&](int t) {
-        const int s = t & 1;
-        mbar_wait(&t_full[s], (t >> 1) & 1);
+        const int s = t % NST;
+        mbar_wait(&t_full[s], (t / NST) & 1);
         tc_fence_after();
         const uint32_t t1 = smem_u32(sT + s * 2 * STR_BYTES), t2 = t1 + STR_BYTES;
-        const uint32_t x_t = tmem_base + s * 128, y_t = x_t + 64;
+        const uint32_t x_t = tmem_base + (t & 1) * 128, y_t = x_t + 64;
 #pragma unroll
         for (int k = 0; k < ATT_HD / 16; ++k) {
           const uint32_t ro = (k >> 2) * RES_CHUNK + (k & 3) * 32, so = (k >> 2) * STR_CHUNK + (k & 3) * 32;
@@ -194,13 +194,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
           const uint32_t ro = (k >> 2) * RES_CHUNK + (k & 3) * 32, so = (k >> 2) * STR_CHUNK + (k & 3) * 32;
           umma_ss(y_t, make_sdesc_sw128(r2 + ro, 0, 1024), make_sdesc_sw128(t2 + so, 0, 1024), idesc_xy, k > 0);
         }
-        umma_commit(&xy_full[s]);
+        umma_commit(&xy_full[t & 1]);
       };
       mbar_wait(r_full, 0);
       issue_xy(0);
       for (int t = 0; t < n; ++t) {
         if (t + 1 < n) issue_xy(t + 1);
-        const int s = t & 1;
+        const int s = t % NST;
         mbar_wait(pds_full, t & 1);
         tc_fence_after();
         const uint32_t t1 = smem_u32(sT + s * 2 * STR_BYTES), t2 = t1 + STR_BYTES;
@@ -241,8 +241,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       self_delta = (self_pos < p.T) ? p.delta[idx] : 0.f;
     }
 
+    // column vectors (doc ids; for dK/dV also lse, delta of the streamed q rows) are fetched one iteration ahead so
+    // that their global-memory latency is off the critical path
+    auto fetch_col = [&](int t, int32_t& d_out, float& f_out) {
+      const int c = tid & 63, pos = iter_row0(t) + c;
+      const int hs_ = iter_head(t);
+      d_out = -2; f_out = 0.f;
+      if (tid < 64) {
+        d_out = (pos < p.T) ? docb[pos] : -2;
+        if (DKDV) f_out = (pos < p.T) ? p.lse[(int64_t(b) * p.H + hs_) * p.T + pos] * 1.4426950408889634f
+                                      : __int_as_float(0x7f800000);
+      } else if (DKDV) {
+        f_out = (pos < p.T) ? p.delta[(int64_t(b) * p.H + hs_) * p.T + pos] : 0.f;
+      }
+    };
+    int32_t nxt_doc; float nxt_f;
+    fetch_col(0, nxt_doc, nxt_f);
+
     for (int t = 0; t < n; ++t) {
-      const int hs = iter_head(t), c0 = iter_row0(t);
+      const int c0 = iter_row0(t);
       const int sblk = c0 / ATT_BLK;
       // pair of 128-blocks is one document strictly off the diagonal -> no mask arithmetic
       bool full;
@@ -256,14 +273,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       float* col_delta = col + SUB;
       int32_t* col_doc = reinterpret_cast<int32_t*>(col + 2 * SUB);
       {
-        const int c = tid & 63, pos = c0 + c;
-        if (tid < 64) {
-          col_doc[c] = (pos < p.T) ? docb[pos] : -2;
-          if (DKDV) col_lse2[c] = (pos < p.T) ? p.lse[(int64_t(b) * p.H + hs) * p.T + pos] * 1.4426950408889634f
-                                              : __int_as_float(0x7f800000);
-        } else if (DKDV) {
-          col_delta[c] = (pos < p.T) ? p.delta[(int64_t(b) * p.H + hs) * p.T + pos] : 0.f;
-        }
+        const int c = tid & 63;
+        if (tid < 64) { col_doc[c] = nxt_doc; if (DKDV) col_lse2[c] = nxt_f; }
+        else if (DKDV) col_delta[c] = nxt_f;
+        if (t + 1 < n) fetch_col(t + 1, nxt_doc, nxt_f);   // in flight during this iteration's math
       }
       named_bar_sync(1, 128);
 

@@ -18,7 +18,7 @@ namespace tn {
 // RMSNorm forward: one warp per row, whole row cached in registers (NV uint4 vectors per lane).
 // ---------------------------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(const uint4* __restrict__ X, const uint4* __restrict__ R,
+__global__ void __launch_bounds__(256, (NV <= 16) ? 2 : 1) rmsnorm_fwd_kernel(const uint4* __restrict__ X, const uint4* __restrict__ R,
                                                           const void* __restrict__ w, int w_is_f32,
                                                           uint4* __restrict__ S_out, uint4* __restrict__ Y,
                                                           float* __restrict__ rstd_out, int64_t rows, int d,

@@ -118,11 +118,9 @@ def run_step(model, d: dict, meta: dict, B: int, T: int):
     frontend.stack_batch(fb, frames, STACK, STRIDE, True, into=feats, dst_rows=meta["dst_rows"])
     out = model(input_ids=d["input_ids"], input_features=feats.view(B, T, -1), attention_mask=d["attention_mask"],
                 position_ids=d["position_ids"])
-    logits = out.logits
-    V = logits.shape[-1]
-    # pack loss next to the path (ref: touchnet/loss/cross_entropy.py:12-50): torch ops, not part of the v1 kernel set
-    ce = F.cross_entropy(logits.float().view(-1, V), d["labels"].view(-1), reduction="none", ignore_index=-100)
-    loss = (ce / d["sentence_lens"].view(-1).float()).sum() / max(meta["num_sentence"], 1)
+    # pack loss next to the path (ref: touchnet/loss/cross_entropy.py:12-50), fused CUDA (csrc/loss.cu)
+    from touchnet_b200 import loss as tn_loss
+    loss, _ = tn_loss.cross_entropy_loss(out.logits, d["labels"], d["sentence_lens"], meta["num_sentence"])
     loss.backward()
     return loss.detach()
 
@@ -174,34 +172,41 @@ class ClockSampler:
 
 
 class GemmTimer:
-    """CUDA events around every GEMM launch of the timed region (launching stream), summed afterwards."""
+    """CUDA events around every launch of our library in the timed region (on the launching stream), summed per kernel
+    class afterwards.  GEMM launches carry their algorithmic FLOPs."""
 
     def __init__(self):
         self.pairs = []
         self._open = None
 
     def __call__(self, name, phase, args):
-        if name not in ("tn_gemm_bf16", "tn_gemm_swiglu_bf16"):
-            return
         if phase == "pre":
             e = torch.cuda.Event(enable_timing=True)
             e.record()
+            flops = 0.0
             if name == "tn_gemm_bf16":
-                M, N, K = args[11], args[12], args[13]
-                flops = 2.0 * M * N * K
-            else:
-                M, N, K = args[9], args[10], args[11]
-                flops = 4.0 * M * N * K
-            self._open = (e, flops)
+                flops = 2.0 * args[11] * args[12] * args[13]
+            elif name == "tn_gemm_swiglu_bf16":
+                flops = 4.0 * args[9] * args[10] * args[11]
+            self._open = (e, flops, name)
         else:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            self.pairs.append((self._open[0], e1, self._open[1]))
+            self.pairs.append((self._open[0], e1, self._open[1], self._open[2]))
 
     def summary(self):
-        ms = sum(a.elapsed_time(b) for a, b, _ in self.pairs)
-        fl = sum(f for _, _, f in self.pairs)
-        return ms, fl, len(self.pairs)
+        ms = fl = 0.0
+        n = 0
+        for a, b, f, name in self.pairs:
+            if name in ("tn_gemm_bf16", "tn_gemm_swiglu_bf16"):
+                ms += a.elapsed_time(b); fl += f; n += 1
+        return ms, fl, n
+
+    def by_class(self):
+        out = {}
+        for a, b, f, name in self.pairs:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return {k: round(v, 3) for k, v in sorted(out.items(), key=lambda kv: -kv[1])}
 
 
 def attn_flops_fwd_per_layer(doc_lens, H=32, hd=128):
@@ -438,6 +443,7 @@ def main():
         "extras": {"nonpad_tokens_per_step_rank0": meta["nonpad_tokens"], "docs_rank0": len(meta["doc_lens"]),
                    "attn_fwd_tflop_mask_exact_per_step_rank0": attn_fwd / 1e12, "loss": final_loss,
                    "model_tflop_per_step_rank0": gemm_flops / args.steps / 1e12,
+                   "ms_by_entry_point_timed_region": gt.by_class(),
                    "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -90,8 +90,11 @@ int tn_rope_apply_bf16(void* X, int64_t ldx, const void* cos_tab, const void* si
  *   mask: allow[b,q,k] = (q >= k) && doc[b,q] == doc[b,k] && doc[b,q] > 0      (doc = attention_mask ids, int32)
  *   Q [B,T,H,128], K/V [B,T,KV,128], O [B,T,H,128] with strides (elements): token stride ld*, batch stride = T*ld*.
  *   lse [B,H,T] fp32 (natural log; +inf for fully-masked rows whose O is exactly 0).
- *   tn_attn_prep builds the per-(b, q-block) kv ranges (device side, no host sync); meta: int32 [B, ceil(T/128), 4].
+ *   tn_attn_prep builds, on the device with no host sync, the per-block kv/q ranges, a per-row "canonical" flag and
+ *   the per-position document extents [start,end) the kernels mask with; meta: int32 buffer of tn_attn_meta_ints(B,T)
+ *   elements.
  */
+int64_t tn_attn_meta_ints(int B, int T);
 int tn_attn_prep(const int32_t* doc_ids, int32_t* meta, int B, int T, tn_stream_t stream);
 int tn_attn_fwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                      int64_t ldo, float* lse, const int32_t* doc_ids, const int32_t* meta, int B, int T, int H, int KV,
@@ -142,6 +145,19 @@ int tn_feat_stack_f32(const float* feats, const int64_t* frame_offsets, const in
 int tn_embed_add_bf16(const int64_t* input_ids, const void* embed, int embed_is_f32, const void* P, void* E,
                       int32_t* nan_flag, int64_t rows, int d, int64_t vocab, tn_stream_t stream);
 int tn_cast_f32_bf16(const float* src, void* dst, int64_t n, tn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Pack-loss cross-entropy next to the path.  touchnet/loss/__init__.py:7-28 +
+ * touchnet/loss/cross_entropy.py:12-50 + touchnet/utils/metrics.py:26-50, without fp32 logits:
+ *   fwd: lse[r] = logsumexp(logits[r,:]) (fp32), ce[r] = lse[r] - logits[r,label[r]] (0 where label is the ignore
+ *        index, i.e. outside [0,V)), argmax[r] (optional, for the accuracy metric).
+ *   bwd: IN PLACE  logits[r,:] <- (softmax(logits[r,:]) - onehot(label[r])) * scale * grad_scalar[0] / sentence_lens[r]
+ *        (rows with an ignored label become 0).  grad_scalar: device pointer to the upstream scalar gradient (or NULL = 1).
+ */
+int tn_pack_ce_fwd_bf16(const void* logits, int64_t ld, const int64_t* labels, float* lse, float* ce, int32_t* argmax,
+                        int64_t M, int V, tn_stream_t stream);
+int tn_pack_ce_bwd_bf16(void* logits, int64_t ld, const int64_t* labels, const int64_t* sentence_lens, const float* lse,
+                        const float* grad_scalar, float scale, int64_t M, int V, tn_stream_t stream);
 
 #ifdef __cplusplus
 }

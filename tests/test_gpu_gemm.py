@@ -8,7 +8,7 @@ from touchnet_b200 import ops
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(128, 256, 64), (256, 128, 256), (512, 1024, 512), (200, 264, 1040), (1024, 4096, 400), (384, 1024, 4096)]
+SHAPES = [(256, 256, 256), (256, 512, 128), (512, 256, 64), (128, 256, 64), (256, 128, 256), (512, 1024, 512), (200, 264, 1040), (1024, 4096, 400), (384, 1024, 4096)]
 
 
 def _mk(M, N, K, dev):

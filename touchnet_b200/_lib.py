@@ -28,6 +28,7 @@ _SIGNATURES = {
     "tn_rmsnorm_bwd_num_partials": [],
     "tn_rope_table": [_vp, _vp, _f, _vp, _vp, _i64, _i, _vp],
     "tn_rope_apply_bf16": [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp],
+    "tn_attn_meta_ints": [_i, _i],
     "tn_attn_prep": [_vp, _vp, _i, _i, _vp],
     "tn_attn_fwd_bf16": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "tn_attn_bwd_bf16": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64,
@@ -38,8 +39,10 @@ _SIGNATURES = {
     "tn_feat_stack_f32": [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp],
     "tn_embed_add_bf16": [_vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _i64, _vp],
     "tn_cast_f32_bf16": [_vp, _vp, _i64, _vp],
+    "tn_pack_ce_fwd_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _vp],
+    "tn_pack_ce_bwd_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _f, _i64, _i, _vp],
 }
-_RESTYPES = {"tn_last_error": c_char_p}
+_RESTYPES = {"tn_last_error": c_char_p, "tn_attn_meta_ints": c_int64}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["tn_last_error"])
 
@@ -67,7 +70,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
             continue
         fn = getattr(lib, name)  # AttributeError if the .so does not export what the header declares
         fn.argtypes = argtypes
-        fn.restype = c_int
+        fn.restype = _RESTYPES.get(name, c_int)
     _lib = lib
     return lib
 

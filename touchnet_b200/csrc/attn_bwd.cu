@@ -41,6 +41,7 @@ struct BwdSmem {
 struct AttnBwdParams {
   const int32_t* doc;
   const AttnMeta* meta;
+  const AttnSeg* seg;
   const float* lse;
   const float* delta;
   bf16* out1;   // dKdV: dV ; dQ: dQ      (all-masked fast path)
@@ -234,6 +235,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const int32_t res_first = docb[r0];                                            // uniform
     const int32_t res_last = (r0 + ATT_BLK - 1 < p.T) ? docb[r0 + ATT_BLK - 1] : 0;  // uniform
     const uint32_t lane_sel = (quad * 32u) << 16;
+    // canonical rows: the partner positions of this row are one contiguous range (two integer compares per element)
+    //   dK/dV (thread = key k):   queries q in [k, seg_end(k))        dQ (thread = query q): keys k in [seg_start(q), q]
+    const AttnSeg myseg = (self_pos < p.T) ? p.seg[int64_t(b) * p.nblk * ATT_BLK + self_pos] : AttnSeg{self_pos + 1, self_pos};
+    const int range_lo_pos = DKDV ? self_pos : myseg.start;
+    const int range_hi_pos = DKDV ? myseg.end - 1 : self_pos;
+    const uint32_t sPT_u32 = smem_u32(sPT), sDST_u32 = smem_u32(sDST);
     float self_lse2 = 0.f, self_delta = 0.f;
     if (!DKDV) {
       const int64_t idx = (int64_t(b) * p.H + hy) * p.T + self_pos;
@@ -282,6 +289,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
 
       const uint32_t x_t = tmem_base + (t & 1) * 128 + lane_sel, y_t = x_t + 64;
       uint32_t pk[32], dk[32];
+      const int lo = range_lo_pos - c0, hi = range_hi_pos - c0;   // allowed streamed columns: lo <= c <= hi
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t xv[32], yv[32];
@@ -294,15 +302,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int c = half * 32 + i + e;
-            const int col_pos = c0 + c;
             bool ok = true;
             if (!full) {
-              const bool causal = DKDV ? (self_pos <= col_pos) : (col_pos <= self_pos);
-              ok = causal && (col_doc[c] == self_doc) && (self_doc > 0);
+              if (meta.canonical) {
+                ok = (c >= lo) && (c <= hi);
+              } else {
+                const int col_pos = c0 + c;
+                const bool causal = DKDV ? (self_pos <= col_pos) : (col_pos <= self_pos);
+                ok = causal && (col_doc[c] == self_doc) && (self_doc > 0);
+              }
             }
             const float l2 = DKDV ? col_lse2[c] : self_lse2;
             const float dl = DKDV ? col_delta[c] : self_delta;
-            const float pv = ok ? fast_exp2(fmaf(__uint_as_float(xv[i + e]), p.scale_log2, -l2)) : 0.f;
+            const float xs = ok ? __uint_as_float(xv[i + e]) : -INFINITY;       // masked -> exp2(-inf) = 0
+            const float pv = fast_exp2(fmaf(xs, p.scale_log2, -l2));
             pe[e] = pv;
             de[e] = pv * (__uint_as_float(yv[i + e]) - dl);
           }
@@ -313,8 +326,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       if (t > 0) mbar_wait(acc_done, (t - 1) & 1);  // previous accumulate MMAs have consumed the P/dS tiles
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        if (DKDV) *reinterpret_cast<uint4*>(sPT + sw128_off(r, u)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        *reinterpret_cast<uint4*>(sDST + sw128_off(r, u)) = make_uint4(dk[4 * u], dk[4 * u + 1], dk[4 * u + 2], dk[4 * u + 3]);
+        if (DKDV) sts_u4(sPT_u32 + sw128_off(r, u), make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]));
+        sts_u4(sDST_u32 + sw128_off(r, u), make_uint4(dk[4 * u], dk[4 * u + 1], dk[4 * u + 2], dk[4 * u + 3]));
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -343,8 +356,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
           for (int e = 0; e < 4; ++e)
             w[e] = pack_bf16x2(__uint_as_float(o[u * 8 + 2 * e]) * mul, __uint_as_float(o[u * 8 + 2 * e + 1]) * mul);
           const int colx = c4 * 32 + u * 8;
-          *reinterpret_cast<uint4*>(stg + (colx >> 6) * RES_CHUNK + sw128_off(r, (colx & 63) >> 3)) =
-              make_uint4(w[0], w[1], w[2], w[3]);
+          sts_u4(smem_u32(stg) + (colx >> 6) * RES_CHUNK + sw128_off(r, (colx & 63) >> 3), make_uint4(w[0], w[1], w[2], w[3]));
         }
       }
     }
@@ -410,6 +422,7 @@ extern "C" int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64
 
   AttnBwdParams p{};
   p.doc = doc_ids; p.meta = reinterpret_cast<const AttnMeta*>(meta); p.lse = lse; p.delta = delta;
+  p.seg = reinterpret_cast<const AttnSeg*>(meta + attn_meta_seg_off(B, nblk));
   p.B = B; p.T = T; p.H = H; p.KV = KV; p.nblk = nblk;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
 

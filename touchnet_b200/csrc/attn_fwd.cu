@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(1024) attn_canonical_kernel(const int32_t* __r
 
 // one warp per (b, block)
 __global__ void __launch_bounds__(256) attn_meta_kernel(const int32_t* __restrict__ doc, const int32_t* __restrict__ flags,
-                                                        AttnMeta* __restrict__ meta, int B, int T, int nblk) {
+                                                        AttnMeta* __restrict__ meta, AttnSeg* __restrict__ seg, int B,
+                                                        int T, int nblk) {
   const int gw = blockIdx.x * 8 + warp_id();
   if (gw >= B * nblk) return;
   const int b = gw / nblk, blk = gw - b * nblk;
@@ -65,13 +66,17 @@ __global__ void __launch_bounds__(256) attn_meta_kernel(const int32_t* __restric
   }
   AttnMeta m;
   m.canonical = canonical;
-  if (first < 0) {  // nothing but padding
-    m.kv_lo = 0; m.kv_end = 0; m.q_end = 0;
-    if (lane == 0) meta[gw] = m;
-    return;
-  }
-  if (!canonical) {
-    m.kv_lo = 0; m.kv_end = blk + 1; m.q_end = nblk;
+  AttnSeg* segb = seg + (int64_t(b) * nblk + blk) * ATT_BLK;
+  if (first < 0 || !canonical) {
+    // padding-only block, or ids that are not non-decreasing runs: segments are empty / unused (the kernels mask
+    // non-canonical rows element-wise by document id over the whole causal range)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + int(lane) + 32 * i;
+      segb[lane + 32 * i] = AttnSeg{t + 1, t};
+    }
+    if (first < 0) { m.kv_lo = 0; m.kv_end = 0; m.q_end = 0; }
+    else { m.kv_lo = 0; m.kv_end = blk + 1; m.q_end = nblk; }
     if (lane == 0) meta[gw] = m;
     return;
   }
@@ -139,6 +144,55 @@ __global__ void __launch_bounds__(256) attn_meta_kernel(const int32_t* __restric
   }
   m.q_end = (run_end - 1) / ATT_BLK + 1;
   if (lane == 0) meta[gw] = m;
+
+  // ---- per-position document extents [start, end) ----
+  // a run starts at p if p == 0 of the block or id[p] != id[p-1]; it ends after p if id[p+1] != id[p]
+  uint32_t sb[4], eb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pos = int(lane) + 32 * i;
+    const int32_t prev = __shfl_up_sync(0xffffffffu, ids[i], 1);
+    const int32_t prev_w = __shfl_sync(0xffffffffu, ids[i > 0 ? i - 1 : 0], 31);
+    const int32_t next = __shfl_down_sync(0xffffffffu, ids[i], 1);
+    const int32_t next_w = __shfl_sync(0xffffffffu, ids[i < 3 ? i + 1 : 3], 0);
+    const int32_t pv = lane > 0 ? prev : (i > 0 ? prev_w : ids[i] /* block edge: resolved by run_start */);
+    const int32_t nx = lane < 31 ? next : (i < 3 ? next_w : ids[i] /* block edge: resolved by run_end */);
+    sb[i] = __ballot_sync(0xffffffffu, pos > 0 && pv != ids[i]);
+    eb[i] = __ballot_sync(0xffffffffu, pos < ATT_BLK - 1 && nx != ids[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pos = int(lane) + 32 * i;
+    const int t = t0 + pos;
+    AttnSeg sg;
+    if (ids[i] <= 0) { sg.start = t + 1; sg.end = t; }
+    else {
+      // last run boundary at or before pos
+      int st = -1;
+      {
+        const uint32_t mcur = sb[i] & (0xffffffffu >> (31 - lane));
+        if (mcur) st = 32 * i + 31 - __clz(mcur);
+        else {
+#pragma unroll
+          for (int w = 3; w >= 0; --w)
+            if (w < i && st < 0 && sb[w]) st = 32 * w + 31 - __clz(sb[w]);
+        }
+      }
+      sg.start = st >= 0 ? t0 + st : run_start;       // no boundary inside the block: the run began earlier
+      int en = -1;
+      {
+        const uint32_t mcur = eb[i] & (0xffffffffu << lane);
+        if (mcur) en = 32 * i + __ffs(mcur) - 1;
+        else {
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            if (w > i && en < 0 && eb[w]) en = 32 * w + __ffs(eb[w]) - 1;
+        }
+      }
+      sg.end = en >= 0 ? t0 + en + 1 : run_end;        // the run continues past the block (or ends at its last valid id)
+    }
+    segb[pos] = sg;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -162,6 +216,7 @@ struct FwdSmem {
 struct AttnFwdParams {
   const int32_t* doc;
   const AttnMeta* meta;
+  const AttnSeg* seg;
   float* lse;
   bf16* O;       // for the all-padding fast path
   int64_t ldo;
@@ -310,90 +365,90 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float m_run = -INFINITY, l_run = 0.f;
     const float NEG_INF = -INFINITY;
 
+    // canonical rows: keys of row q are exactly the positions [seg_start(q), q]  -> two integer compares per element;
+    // non-canonical rows: exact element-wise document-id compare (ids staged in smem)
+    const AttnSeg myseg = (qpos < p.T) ? p.seg[int64_t(b) * p.nblk * ATT_BLK + qpos] : AttnSeg{qpos + 1, qpos};
+    const uint32_t sP_u32 = smem_u32(sP);
+    const uint32_t sDocK_u32 = smem_u32(sDocK);
+
     for (int j = 0; j < n; ++j) {
       const int kb = kv_lo + j;
       const int k0 = kb * ATT_BLK;
       // block needs no mask iff strictly below the diagonal and one document spans [k0, q0+127]
       const bool full = meta.canonical && (kb < qb) && (dq_last > 0) && (docb[k0] == dq_last);
-      int32_t* dk = sDocK + (j & 1) * 128;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      // (S_j complete implies every thread finished block j-2, the previous user of this dk buffer)
-      if (!full) {
-        dk[tid] = (k0 + tid < p.T) ? docb[k0 + tid] : -1;
+      const uint32_t dk_u32 = sDocK_u32 + (j & 1) * 512;
+      if (!meta.canonical) {
+        // (S_j complete implies every thread finished block j-2, the previous user of this buffer)
+        sts_u32(dk_u32 + tid * 4, uint32_t((k0 + tid < p.T) ? docb[k0 + tid] : -1));
         named_bar_sync(1, 128);
       }
       const uint32_t s_addr = tmem_S + (j & 1) * 128 + lane_sel;
 
-      // ---- pass 1: row max of the masked, scaled scores ----
+      // ---- one TMEM pass: the whole 128-wide score row lives in registers ----
+      uint32_t v[4][32];
+      tmem_ld32(s_addr, v[0]);
+      tmem_ld32(s_addr + 32, v[1]);
+      tmem_ld32(s_addr + 64, v[2]);
+      tmem_ld32(s_addr + 96, v[3]);
+      tmem_ld_wait();
       float mx = NEG_INF;
-#pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t v[32];
-        tmem_ld32(s_addr + c4 * 32, v);
-        tmem_ld_wait();
-        if (full) {
+      if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+        for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c4][i]));
+      } else if (meta.canonical) {
+        const int lo = myseg.start - k0, hi = qpos - k0;   // allowed columns: lo <= c <= hi
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = c4 * 32 + i;
+            const float x = (c >= lo && c <= hi) ? __uint_as_float(v[c4][i]) : NEG_INF;
+            v[c4][i] = __float_as_uint(x);
+            mx = fmaxf(mx, x);
+          }
+      } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
-            const int4 d4 = *reinterpret_cast<const int4*>(dk + c4 * 32 + i4 * 4);
-            const int32_t dd[4] = {d4.x, d4.y, d4.z, d4.w};
+            const uint4 d4 = lds_u4(dk_u32 + (c4 * 32 + i4 * 4) * 4);
+            const int32_t dd[4] = {int32_t(d4.x), int32_t(d4.y), int32_t(d4.z), int32_t(d4.w)};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c = c4 * 32 + i4 * 4 + e;
               const bool ok = (k0 + c <= qpos) && (dd[e] == dq) && (dq > 0);
-              if (ok) mx = fmaxf(mx, __uint_as_float(v[i4 * 4 + e]));
+              const float x = ok ? __uint_as_float(v[c4][i4 * 4 + e]) : NEG_INF;
+              v[c4][i4 * 4 + e] = __float_as_uint(x);
+              mx = fmaxf(mx, x);
             }
           }
-        }
       }
-      mx *= p.scale_log2;  // scale > 0, so max commutes with the scaling (−inf stays −inf)
+      mx *= p.scale_log2;  // scale > 0, so max commutes with the scaling (-inf stays -inf)
       // lazy rescale: keep the old reference max unless it grew by more than 2^8
       float m_new = m_run, alpha = 1.f;
       if (mx > m_run + 8.f || (m_run == NEG_INF && mx > NEG_INF)) {
         m_new = mx;
-        alpha = fast_exp2(m_run - m_new);  // m_run = −inf -> 0
+        alpha = fast_exp2(m_run - m_new);  // m_run = -inf -> 0
       }
       const float m_use = (m_new == NEG_INF) ? 0.f : m_new;
 
-      // ---- pass 2: p = exp2(s*scale − m), packed to bf16 ----
-      uint32_t pk[64];
-      float psum = 0.f;
+      // ---- p = exp2(s*scale - m) (masked entries are -inf -> 0), packed to bf16 in place ----
+      float psum0 = 0.f, psum1 = 0.f;
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t v[32];
-        tmem_ld32(s_addr + c4 * 32, v);
-        tmem_ld_wait();
-        if (full) {
+      for (int c4 = 0; c4 < 4; ++c4)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_use));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_use));
-            psum += p0 + p1;
-            pk[c4 * 16 + i] = pack_bf16x2(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const int4 d4 = *reinterpret_cast<const int4*>(dk + c4 * 32 + i4 * 4);
-            const int32_t dd[4] = {d4.x, d4.y, d4.z, d4.w};
-            float pe[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = c4 * 32 + i4 * 4 + e;
-              const bool ok = (k0 + c <= qpos) && (dd[e] == dq) && (dq > 0);
-              const float x = fmaf(__uint_as_float(v[i4 * 4 + e]), p.scale_log2, -m_use);
-              pe[e] = ok ? fast_exp2(x) : 0.f;
-            }
-            psum += (pe[0] + pe[1]) + (pe[2] + pe[3]);
-            pk[c4 * 16 + i4 * 2] = pack_bf16x2(pe[0], pe[1]);
-            pk[c4 * 16 + i4 * 2 + 1] = pack_bf16x2(pe[2], pe[3]);
-          }
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[c4][2 * i]), p.scale_log2, -m_use));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[c4][2 * i + 1]), p.scale_log2, -m_use));
+          psum0 += p0;
+          psum1 += p1;
+          v[c4][i] = pack_bf16x2(p0, p1);   // slot i <= 2i: already consumed
         }
-      }
-      l_run = l_run * alpha + psum;
+      l_run = l_run * alpha + (psum0 + psum1);
       m_run = m_new;
 
       // ---- wait for the previous PV (frees P smem and makes O consistent), rescale O if any row needs it ----
@@ -413,16 +468,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_st_wait();
         }
       }
-      // ---- P -> smem (K-major, 128B swizzle) ----
+      // ---- P -> smem (K-major, 128B swizzle): columns 32*c4 + [0,32) are packed words v[c4][0..15] ----
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      for (int c4 = 0; c4 < 4; ++c4)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int w = ch * 32 + u * 4;
-          *reinterpret_cast<uint4*>(sP + ch * CHUNK_BYTES + sw128_off(r, u)) =
-              make_uint4(pk[w], pk[w + 1], pk[w + 2], pk[w + 3]);
+        for (int q = 0; q < 4; ++q) {
+          const int u = (c4 & 1) * 4 + q;   // 16-byte unit inside the 64-column chunk
+          sts_u4(sP_u32 + (c4 >> 1) * CHUNK_BYTES + sw128_off(r, u),
+                 make_uint4(v[c4][4 * q], v[c4][4 * q + 1], v[c4][4 * q + 2], v[c4][4 * q + 3]));
         }
-      }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
@@ -444,8 +498,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int e = 0; e < 4; ++e)
           w[e] = pack_bf16x2(__uint_as_float(o[u * 8 + 2 * e]) * inv_l, __uint_as_float(o[u * 8 + 2 * e + 1]) * inv_l);
         const int col = c4 * 32 + u * 8;  // 0..127
-        *reinterpret_cast<uint4*>(sP + (col >> 6) * CHUNK_BYTES + sw128_off(r, (col & 63) >> 3)) =
-            make_uint4(w[0], w[1], w[2], w[3]);
+        sts_u4(sP_u32 + (col >> 6) * CHUNK_BYTES + sw128_off(r, (col & 63) >> 3), make_uint4(w[0], w[1], w[2], w[3]));
       }
     }
     if (qpos < p.T)
@@ -473,17 +526,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 using namespace tn;
 
+extern "C" int64_t tn_attn_meta_ints(int B, int T) {
+  return attn_meta_total(B, (T + ATT_BLK - 1) / ATT_BLK);
+}
+
 extern "C" int tn_attn_prep(const int32_t* doc_ids, int32_t* meta, int B, int T, tn_stream_t stream_) {
   clear_error();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TN_REQUIRE(doc_ids && meta, "tn_attn_prep: null pointer");
   TN_REQUIRE(B > 0 && T > 0, "tn_attn_prep: empty batch");
   const int nblk = (T + ATT_BLK - 1) / ATT_BLK;
-  int32_t* flags = meta + int64_t(B) * nblk * 4;
+  int32_t* flags = meta + attn_meta_flags_off(B, nblk);
+  AttnSeg* seg = reinterpret_cast<AttnSeg*>(meta + attn_meta_seg_off(B, nblk));
   attn_canonical_kernel<<<B, 1024, 0, stream>>>(doc_ids, flags, T);
   TN_CHECK_CUDA(cudaGetLastError());
   const int warps = B * nblk;
-  attn_meta_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(doc_ids, flags, reinterpret_cast<AttnMeta*>(meta), B, T, nblk);
+  attn_meta_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(doc_ids, flags, reinterpret_cast<AttnMeta*>(meta), seg, B, T, nblk);
   TN_CHECK_CUDA(cudaGetLastError());
   return TN_OK;
 }
@@ -507,6 +565,7 @@ extern "C" int tn_attn_fwd_bf16(const void* Q, int64_t ldq, const void* K, int64
   if ((rc = encode_tmap_3d(&tmO, O, 2, uint64_t(H) * ATT_HD, T, B, ldo * 2, uint64_t(T) * ldo * 2, 64, ATT_BLK, 1, true))) return rc;
   AttnFwdParams p{};
   p.doc = doc_ids; p.meta = reinterpret_cast<const AttnMeta*>(meta); p.lse = lse;
+  p.seg = reinterpret_cast<const AttnSeg*>(meta + attn_meta_seg_off(B, nblk));
   p.O = static_cast<bf16*>(O); p.ldo = ldo;
   p.B = B; p.T = T; p.H = H; p.KV = KV; p.nblk = nblk;
   p.scale_log2 = scale * 1.4426950408889634f;

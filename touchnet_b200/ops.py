@@ -188,8 +188,8 @@ class AttnPlan:
         assert doc_ids.dim() == 2
         self.B, self.T = doc_ids.shape
         self.doc = doc_ids.to(torch.int32).contiguous()
-        nblk = (self.T + 127) // 128
-        self.meta = torch.empty(self.B * nblk * 4 + self.B, dtype=torch.int32, device=doc_ids.device)
+        n_ints = int(_lib.load().tn_attn_meta_ints(self.B, self.T))
+        self.meta = torch.empty(n_ints, dtype=torch.int32, device=doc_ids.device)
         _lib.call("tn_attn_prep", self.doc.data_ptr(), self.meta.data_ptr(), self.B, self.T, _st())
 
 

@@ -17,7 +17,7 @@
 
 namespace tn {
 
-constexpr int BWD_THREADS = 192;
+constexpr int BWD_THREADS = 320;                      // TMA warp, MMA warp, 2 softmax-grad warpgroups (ping-pong)
 constexpr int SUB = 64;                               // streamed rows per iteration
 constexpr int RES_BYTES = ATT_BLK * ATT_HD * 2;       // 32 KB resident tile (2 chunks of 16 KB)
 constexpr int RES_CHUNK = RES_BYTES / 2;
@@ -30,9 +30,9 @@ struct BwdSmem {
   static constexpr int R1 = 0;
   static constexpr int R2 = R1 + RES_BYTES;
   static constexpr int T = R2 + RES_BYTES;                  // NST stages x (T1, T2)
-  static constexpr int PT = T + NST * 2 * STR_BYTES;
-  static constexpr int DST = PT + PT_BYTES;
-  static constexpr int COL = DST + PT_BYTES;                // 2 x {lse2[64], delta[64], doc[64]}
+  static constexpr int PT = T + NST * 2 * STR_BYTES;         // 2 buffers (one per warpgroup)
+  static constexpr int DST = PT + 2 * PT_BYTES;             // 2 buffers
+  static constexpr int COL = DST + 2 * PT_BYTES;            // 2 x {lse2[64], delta[64], doc[64]}
   static constexpr int BARS = COL + 2 * 3 * SUB * 4;
   static constexpr int TOTAL = BARS + 256;
   static constexpr int ALLOC = TOTAL + 1024;
@@ -98,9 +98,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   uint64_t* t_full = bars + 1;    // [NST]
   uint64_t* t_empty = bars + 5;   // [NST]
   uint64_t* xy_full = bars + 9;   // [2]
-  uint64_t* pds_full = bars + 11;
-  uint64_t* acc_done = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* pds_full = bars + 11; // [2]
+  uint64_t* acc_done = bars + 13; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const uint32_t warp = warp_id(), lane = lane_id();
   const int blk = DKDV ? int(blockIdx.x) : p.nblk - 1 - int(blockIdx.x);
@@ -135,9 +135,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   if (warp == 1 && lane == 0) {
     mbar_init(r_full, 1);
     for (int s = 0; s < NST; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) mbar_init(&xy_full[s], 1);
-    mbar_init(pds_full, 128);
-    mbar_init(acc_done, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&xy_full[s], 1); mbar_init(&pds_full[s], 128); mbar_init(&acc_done[s], 1); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -178,7 +176,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc_xy = make_idesc_bf16(128, SUB, 0, 0);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, ATT_HD, 0, 1);
-      const uint32_t r1 = smem_u32(sR1), r2 = smem_u32(sR2), pt = smem_u32(sPT), dst = smem_u32(sDST);
+      const uint32_t r1 = smem_u32(sR1), r2 = smem_u32(sR2), pt0 = smem_u32(sPT), dst0 = smem_u32(sDST);
       auto issue_xy = [&](int t) {
         const int s = t % NST;
         mbar_wait(&t_full[s], (t / NST) & 1);
@@ -202,9 +200,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       for (int t = 0; t < n; ++t) {
         if (t + 1 < n) issue_xy(t + 1);
         const int s = t % NST;
-        mbar_wait(pds_full, t & 1);
+        mbar_wait(&pds_full[t & 1], (t >> 1) & 1);
         tc_fence_after();
         const uint32_t t1 = smem_u32(sT + s * 2 * STR_BYTES), t2 = t1 + STR_BYTES;
+        const uint32_t pt = pt0 + (t & 1) * PT_BYTES, dst = dst0 + (t & 1) * PT_BYTES;
 #pragma unroll
         for (int k = 0; k < SUB / 16; ++k) {
           if (DKDV) {
@@ -220,15 +219,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
           }
         }
         umma_commit(&t_empty[s]);
-        umma_commit(acc_done);
+        umma_commit(&acc_done[t & 1]);
       }
     }
     __syncwarp();
   } else {
     // ===================== softmax-grad warps: thread = resident row =====================
+    // two warpgroups: group g handles iterations t = g, g+2, ... (its own score buffer, P/dS tiles, column vectors and
+    // named barrier), so one group's exp/convert work overlaps the other's and the tensor pipe sees back-to-back MMAs
+    const int grp = (int(warp) - 2) >> 2;
     const uint32_t quad = warp & 3u;
     const uint32_t r = quad * 32 + lane;
-    const int tid = int(threadIdx.x) - 64;
+    const int tid = int(threadIdx.x) - 64 - 128 * grp;
     const int self_pos = r0 + int(r);
     const int32_t* docb = p.doc + int64_t(b) * p.T;
     const int32_t self_doc = (self_pos < p.T) ? docb[self_pos] : 0;
@@ -240,7 +242,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const AttnSeg myseg = (self_pos < p.T) ? p.seg[int64_t(b) * p.nblk * ATT_BLK + self_pos] : AttnSeg{self_pos + 1, self_pos};
     const int range_lo_pos = DKDV ? self_pos : myseg.start;
     const int range_hi_pos = DKDV ? myseg.end - 1 : self_pos;
-    const uint32_t sPT_u32 = smem_u32(sPT), sDST_u32 = smem_u32(sDST);
+    const uint32_t sPT_u32 = smem_u32(sPT) + grp * PT_BYTES, sDST_u32 = smem_u32(sDST) + grp * PT_BYTES;
     float self_lse2 = 0.f, self_delta = 0.f;
     if (!DKDV) {
       const int64_t idx = (int64_t(b) * p.H + hy) * p.T + self_pos;
@@ -262,10 +264,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         f_out = (pos < p.T) ? p.delta[(int64_t(b) * p.H + hs_) * p.T + pos] : 0.f;
       }
     };
-    int32_t nxt_doc; float nxt_f;
-    fetch_col(0, nxt_doc, nxt_f);
+    int32_t nxt_doc = -2; float nxt_f = 0.f;
+    if (grp < n) fetch_col(grp, nxt_doc, nxt_f);
 
-    for (int t = 0; t < n; ++t) {
+    for (int t = grp; t < n; t += 2) {
       const int c0 = iter_row0(t);
       const int sblk = c0 / ATT_BLK;
       // pair of 128-blocks is one document strictly off the diagonal -> no mask arithmetic
@@ -283,9 +285,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         const int c = tid & 63;
         if (tid < 64) { col_doc[c] = nxt_doc; if (DKDV) col_lse2[c] = nxt_f; }
         else if (DKDV) col_delta[c] = nxt_f;
-        if (t + 1 < n) fetch_col(t + 1, nxt_doc, nxt_f);   // in flight during this iteration's math
+        if (t + 2 < n) fetch_col(t + 2, nxt_doc, nxt_f);   // in flight during this iteration's math
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1 + grp, 128);
 
       const uint32_t x_t = tmem_base + (t & 1) * 128 + lane_sel, y_t = x_t + 64;
       uint32_t pk[32], dk[32];
@@ -323,7 +325,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
           dk[(half * 32 + i) >> 1] = pack_bf16x2(de[0], de[1]);
         }
       }
-      if (t > 0) mbar_wait(acc_done, (t - 1) & 1);  // previous accumulate MMAs have consumed the P/dS tiles
+      if (t >= 2) mbar_wait(&acc_done[t & 1], ((t >> 1) - 1) & 1);  // MMAs of iteration t-2 have consumed this group's tiles
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         if (DKDV) sts_u4(sPT_u32 + sw128_off(r, u), make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]));
@@ -331,19 +333,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(pds_full);
+      mbar_arrive(&pds_full[t & 1]);
     }
 
     // ---- epilogue: accumulators -> bf16 -> smem staging (streamed-tile ring is idle now) -> TMA store ----
-    mbar_wait(acc_done, (n - 1) & 1);
+    // group 0 writes accumulator 1 (dV | dQ), group 1 accumulator 2 (dK)
+    mbar_wait(&acc_done[(n - 1) & 1], ((n - 1) >> 1) & 1);
     tc_fence_after();
-    uint8_t* stage1 = sT;
-    uint8_t* stage2 = sT + RES_BYTES;
-#pragma unroll
-    for (int a = 0; a < (DKDV ? 2 : 1); ++a) {
-      const uint32_t acc_t = (a == 0 ? tmem_acc1 : tmem_acc2) + lane_sel;
-      uint8_t* stg = a == 0 ? stage1 : stage2;
-      const float mul = (DKDV && a == 0) ? 1.f : p.scale;  // dV unscaled; dK, dQ carry the softmax scale
+    if (DKDV || grp == 0) {
+      const uint32_t acc_t = (grp == 0 ? tmem_acc1 : tmem_acc2) + lane_sel;
+      uint8_t* stg = sT + grp * RES_BYTES;
+      const float mul = (DKDV && grp == 0) ? 1.f : p.scale;  // dV unscaled; dK, dQ carry the softmax scale
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         uint32_t o[32];
@@ -359,18 +359,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
           sts_u4(smem_u32(stg) + (colx >> 6) * RES_CHUNK + sw128_off(r, (colx & 63) >> 3), make_uint4(w[0], w[1], w[2], w[3]));
         }
       }
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1, 128);
-    if (tid == 0) {
-      tma_store_3d(&tmOut1, stage1, hy * ATT_HD, r0, b);
-      tma_store_3d(&tmOut1, stage1 + RES_CHUNK, hy * ATT_HD + 64, r0, b);
-      if (DKDV) {
-        tma_store_3d(&tmOut2, stage2, hy * ATT_HD, r0, b);
-        tma_store_3d(&tmOut2, stage2 + RES_CHUNK, hy * ATT_HD + 64, r0, b);
+      fence_proxy_async_smem();
+      named_bar_sync(1 + grp, 128);
+      if (tid == 0) {
+        const CUtensorMap* tmo = (grp == 0) ? &tmOut1 : &tmOut2;
+        tma_store_3d(tmo, stg, hy * ATT_HD, r0, b);
+        tma_store_3d(tmo, stg + RES_CHUNK, hy * ATT_HD + 64, r0, b);
+        tma_store_commit();
+        tma_store_wait_read<0>();
       }
-      tma_store_commit();
-      tma_store_wait_read<0>();
     }
   }
 

@@ -188,6 +188,8 @@ class GemmTimer:
                 flops = 2.0 * args[11] * args[12] * args[13]
             elif name == "tn_gemm_swiglu_bf16":
                 flops = 4.0 * args[9] * args[10] * args[11]
+            elif name == "tn_gemm_qkv_bf16":
+                flops = 2.0 * args[15] * args[16] * args[17]
             self._open = (e, flops, name)
         else:
             e1 = torch.cuda.Event(enable_timing=True)
@@ -198,7 +200,7 @@ class GemmTimer:
         ms = fl = 0.0
         n = 0
         for a, b, f, name in self.pairs:
-            if name in ("tn_gemm_bf16", "tn_gemm_swiglu_bf16"):
+            if name in ("tn_gemm_bf16", "tn_gemm_swiglu_bf16", "tn_gemm_qkv_bf16"):
                 ms += a.elapsed_time(b); fl += f; n += 1
         return ms, fl, n
 
@@ -312,7 +314,8 @@ def workload_config(args, n):
                         f"ffn=14336 V=128256, projector {MEL * STACK}->4096), audio+text packed rows, fbank80 stack{STACK}/"
                         f"stride{STRIDE} frontend on GPU, fwd+bwd, fp32 master weights + fp32 weight grads",
             "global_batch": args.batch * n, "seq_len": args.seq_len,
-            "parallelism": "single GPU" if n == 1 else f"FSDP2 dp_shard={n} (bf16 params / fp32 reduce)",
+            "parallelism": "single GPU" if n == 1 else f"FSDP2 dp_shard={n} (bf16 params / fp32 reduce), "
+                           f"{os.environ.get('TN_SM_MARGIN', '16')} SMs left to NCCL",
             "l2_policy": "inputs larger than L2: every step streams >16 GB of weights through a 126 MB L2"}
 
 
@@ -341,6 +344,8 @@ def main():
 
     from touchnet_b200 import _lib, modeling, ops
     _lib.load()
+    sm_margin = int(os.environ.get("TN_SM_MARGIN", "16" if world > 1 else "0"))
+    _lib.call("tn_set_sm_margin", sm_margin)   # leave SMs to the FSDP2 NCCL kernels so that they overlap the GEMMs
     B, T = args.batch, args.seq_len
     cfg = asr_config(args.layers)
 

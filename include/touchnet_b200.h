@@ -30,6 +30,10 @@ const char* tn_last_error(void);
 int tn_version(void);
 /* 0 iff the current CUDA device is compute capability 10.x (B200). */
 int tn_device_check(void);
+/* Persistent kernels (the GEMMs) launch one CTA per SM; under FSDP2 the NCCL all-gather / reduce-scatter kernels of the
+ * neighbouring layers need SMs of their own to overlap with them.  Leave `sms` SMs unused by persistent grids
+ * (0 = default, single GPU).  Process-wide. */
+int tn_set_sm_margin(int sms);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GEMM  D[M,N] = A·Bᵀ (+ R)          tcgen05 / TMEM / TMA, bf16 in, fp32 accumulate.
@@ -49,6 +53,15 @@ int tn_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
  * Reference interface: hf:models/llama/modeling_llama.py:182-184 LlamaMLP.forward (gate_proj, up_proj, act_fn, mul). */
 int tn_gemm_swiglu_bf16(const void* X, int64_t ldx, const void* Wg, const void* Wu, int64_t ldw, void* G, void* U,
                         void* H, int64_t ldh, int M, int N, int K, tn_stream_t stream);
+
+/* q/k/v projections as ONE launch although the three weights stay separate parameters (HF FQNs, FSDP2, DCP):
+ *   mode 0 forward  D0[M, s0+s1+s2] = A[M,K] · [B0;B1;B2]ᵀ         (B_i [s_i, K]; q|k|v land side by side in one buffer)
+ *   mode 1 dgrad    D0[M, N]        = A[M, s0+s1+s2] · [B0;B1;B2]   (A = dq|dk|dv side by side; B_i [s_i, N])
+ *   mode 2 wgrad    D_i[s_i, N]     = A[:, seg_i]ᵀ · B0[Mred=K, N]  (A = dq|dk|dv [K, s0+s1+s2]; B0 = layer input x)
+ * Segment sizes must be multiples of 256.  hf:models/llama/modeling_llama.py:251-289 (q_proj, k_proj, v_proj). */
+int tn_gemm_qkv_bf16(int mode, const void* A, int64_t lda, const void* B0, const void* B1, const void* B2, int64_t ldb,
+                     void* D0, void* D1, void* D2, int64_t ldd, int d_f32, int s0, int s1, int s2, int M, int N, int K,
+                     tn_stream_t stream);
 
 /* SwiGLU backward (elementwise): dG = dH⊙U⊙silu'(G), dU = dH⊙silu(G).  bf16 [M,N] contiguous rows (ld). */
 int tn_swiglu_bwd_bf16(const void* G, const void* U, const void* dH, void* dG, void* dU, int64_t rows, int64_t cols,

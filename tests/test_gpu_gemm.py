@@ -77,3 +77,30 @@ def test_gemm_rejects_bad_arguments():
         ops.gemm(a, b)
     with pytest.raises(TouchNetB200Error):
         ops.gemm(torch.zeros(8, 8), torch.zeros(8, 8))             # CPU tensors: no CPU path
+
+
+@pytest.mark.parametrize("M,d,nq,nkv", [(512, 512, 512, 256), (8192, 4096, 4096, 1024), (300, 1024, 256, 256)])
+def test_fused_qkv_projection_forward_dgrad_wgrad(M, d, nq, nkv):
+    """One-launch q/k/v projection with three separate weight tensors (segmented operands) == three separate GEMMs."""
+    dev = require_cuda()
+    torch.manual_seed(M + d)
+    x = (torch.randn(M, d, device=dev) * 0.5).bfloat16()
+    wq = (torch.randn(nq, d, device=dev) * 0.05).bfloat16()
+    wk = (torch.randn(nkv, d, device=dev) * 0.05).bfloat16()
+    wv = (torch.randn(nkv, d, device=dev) * 0.05).bfloat16()
+    assert ops.qkv_fusable(M, nq, nkv)
+    qkv = ops.gemm_qkv_fwd(x, wq, wk, wv)
+    ref = torch.cat([ops.gemm(x, wq), ops.gemm(x, wk), ops.gemm(x, wv)], dim=1)
+    assert torch.equal(qkv, ref)                                   # same tiles, same k order: bit identical
+    dqkv = (torch.randn(M, nq + 2 * nkv, device=dev) * 0.1).bfloat16()
+    dx = ops.gemm_qkv_dgrad(dqkv, wq, wk, wv)
+    dx_ref = dqkv.float() @ torch.cat([wq, wk, wv]).float()
+    assert float((dx.float() - dx_ref).abs().max()) < 1e-2 * float(dx_ref.abs().max()) + 1e-2
+    wq32, wk32, wv32 = wq.float(), wk.float(), wv.float()          # fp32 masters -> fp32 gradients
+    dws = ops.gemm_qkv_wgrad(dqkv, x, wq32, wk32, wv32)
+    offs = [0, nq, nq + nkv, nq + 2 * nkv]
+    for i, dw in enumerate(dws):
+        want = dqkv[:, offs[i]:offs[i + 1]].float().t() @ x.float()
+        assert dw.dtype == torch.float32 and float((dw - want).abs().max()) < 1e-4 * float(want.abs().max()) + 1e-4
+    dws_b = ops.gemm_qkv_wgrad(dqkv, x, wq, wk, wv)                 # bf16 parameters (FSDP2 mixed precision)
+    assert all(t.dtype == torch.bfloat16 for t in dws_b)

@@ -20,8 +20,10 @@ _vp, _i, _i64, _f = c_void_p, c_int, c_int64, c_float
 _SIGNATURES = {
     "tn_version": [],
     "tn_device_check": [],
+    "tn_set_sm_margin": [_i],
     "tn_gemm_bf16": [_vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _vp],
     "tn_gemm_swiglu_bf16": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
+    "tn_gemm_qkv_bf16": [_i, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp],
     "tn_swiglu_bwd_bf16": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     "tn_rmsnorm_fwd_bf16": [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _f, _vp],
     "tn_rmsnorm_bwd_bf16": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i64, _i, _vp],

@@ -340,6 +340,8 @@ int gemm_pair_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int6
                        int d_f32, const void* R, int64_t ldr, int M, int N, int K, cudaStream_t stream);
 int gemm_pair_swiglu_dispatch(const void* X, int64_t ldx, const void* Wg, const void* Wu, int64_t ldw, void* G, void* U,
                               void* H, int64_t ldh, int M, int N, int K, cudaStream_t stream);
+int gemm_pair_seg_dispatch(int mode, const void* A, int64_t lda, const void* const* Bs, int64_t ldb, void* const* Ds,
+                           int64_t ldd, int d_f32, const int* seg, int M, int N, int K, cudaStream_t stream);
 // TN_GEMM_PAIR=0 forces the single-CTA kernels (A/B measurements); default: CTA pairs whenever the tile fits
 static bool use_pair() {
   static int v = -1;
@@ -425,4 +427,26 @@ extern "C" int tn_gemm_swiglu_bf16(const void* X, int64_t ldx, const void* Wg, c
   rc = encode_tmap_2d(&tmU, Wu, 2, uint64_t(K), uint64_t(N), uint64_t(ldw) * 2, 64, BN / 2, true);
   if (rc) return rc;
   return launch_gemm<BN, false, false, 1>(tmA, tmG, tmU, p, stream);
+}
+
+extern "C" int tn_gemm_qkv_bf16(int mode, const void* A, int64_t lda, const void* B0, const void* B1, const void* B2,
+                                int64_t ldb, void* D0, void* D1, void* D2, int64_t ldd, int d_f32, int s0, int s1, int s2,
+                                int M, int N, int K, tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(A && B0 && D0, "tn_gemm_qkv_bf16: null pointer");
+  TN_REQUIRE(mode >= 0 && mode <= 2, "tn_gemm_qkv_bf16: mode must be 0 (forward), 1 (dgrad) or 2 (wgrad)");
+  TN_REQUIRE(s0 > 0 && s1 > 0 && s2 > 0 && s0 % 256 == 0 && s1 % 256 == 0 && s2 % 256 == 0,
+             "tn_gemm_qkv_bf16: segment sizes (%d,%d,%d) must be positive multiples of 256", s0, s1, s2);
+  const int tot = s0 + s1 + s2;
+  TN_REQUIRE((mode == 0 && N == tot) || (mode == 1 && K == tot) || (mode == 2 && M == tot),
+             "tn_gemm_qkv_bf16: segments do not add up to the segmented dimension");
+  TN_REQUIRE(M >= 256 && N >= 256 && lda % 8 == 0 && ldb % 8 == 0 && ldd % (d_f32 ? 4 : 8) == 0,
+             "tn_gemm_qkv_bf16: needs M,N >= 256 and 16-byte aligned leading dimensions");
+  TN_REQUIRE(mode == 2 || (B1 && B2), "tn_gemm_qkv_bf16: B1/B2 required");
+  TN_REQUIRE(mode != 2 || (D1 && D2), "tn_gemm_qkv_bf16: D1/D2 required for wgrad");
+  const void* Bs[3] = {B0, B1, B2};
+  void* Ds[3] = {D0, D1, D2};
+  const int seg[3] = {s0, s1, s2};
+  return gemm_pair_seg_dispatch(mode, A, lda, Bs, ldb, Ds, ldd, d_f32, seg, M, N, K, stream);
 }

@@ -36,6 +36,12 @@ struct PairParams {
   int num_m, num_n, num_k;   // num_m in units of 256 rows
   const void* R;
   int64_t ldr;
+  // segmented operands: several weight tensors that are separate nn.Parameters (q/k/v projections) behave as one GEMM
+  //   b_seg 1: B = [B0;B1;B2] stacked along N (fused QKV forward)       -> D columns [0,off1) [off1,off2) [off2,N)
+  //   b_seg 2: B = [B0;B1;B2] stacked along K (fused QKV dgrad)         -> A columns ...
+  //   d_seg 1: D = [D0;D1;D2] stacked along M (fused QKV wgrad: one dW per parameter)
+  int b_seg, d_seg;
+  int off1, off2;
 };
 
 __device__ __forceinline__ void pair_decode_tile(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
@@ -54,7 +60,8 @@ __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.syn
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD,
+                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmB3,
+                 const __grid_constant__ CUtensorMap tmD,
                  const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3, const PairParams p) {
   using Cfg = PairCfg<EPI>;
   constexpr int STAGES = Cfg::STAGES;
@@ -77,6 +84,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmD);
+    if (p.b_seg) { tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmB3); }
+    if (p.d_seg) { tma_prefetch_desc(&tmD2); tma_prefetch_desc(&tmD3); }
     if (EPI == 1) { tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmD2); tma_prefetch_desc(&tmD3); }
   }
   if (warp == 1 && lane == 0) {
@@ -101,13 +110,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int m_blk, n_blk;
         pair_decode_tile(tile, p.num_m, p.num_n, m_blk, n_blk);
         const int m0 = m_blk * 256 + int(rank) * P_BM;
-        const int n0 = (EPI == 1) ? n_blk * 128 : n_blk * P_BN + int(rank) * (P_BN / 2);
+        int n0 = (EPI == 1) ? n_blk * 128 : n_blk * P_BN + int(rank) * (P_BN / 2);
+        const CUtensorMap* bmap = &tmB;
+        if (EPI != 1 && p.b_seg == 1) {   // weight segment that owns these 128 output columns
+          const int sg = (n0 >= p.off1) + (n0 >= p.off2);
+          bmap = sg == 0 ? &tmB : (sg == 1 ? &tmB2 : &tmB3);
+          n0 -= sg == 0 ? 0 : (sg == 1 ? p.off1 : p.off2);
+        }
         for (int kb = 0; kb < p.num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
           uint8_t* a_dst = sA + stage * P_A_BYTES;
           uint8_t* b_dst = sB + stage * P_B_BYTES;
           const int k0 = kb * P_BK;
+          int kb0 = k0;   // k coordinate inside the selected B segment
+          if (EPI != 1 && p.b_seg == 2) {
+            const int sg = (k0 >= p.off1) + (k0 >= p.off2);
+            bmap = sg == 0 ? &tmB : (sg == 1 ? &tmB2 : &tmB3);
+            kb0 = k0 - (sg == 0 ? 0 : (sg == 1 ? p.off1 : p.off2));
+          }
           if (!A_MN) {
             tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], k0, m0);
           } else {
@@ -117,10 +138,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (EPI == 1) {
             tma_load_2d_pair(b_dst, rank == 0 ? &tmB : &tmB2, &full_bar[stage], k0, n0);  // CTA0: gate rows, CTA1: up rows
           } else if (!B_MN) {
-            tma_load_2d_pair(b_dst, &tmB, &full_bar[stage], k0, n0);
+            tma_load_2d_pair(b_dst, bmap, &full_bar[stage], kb0, n0);
           } else {
-            tma_load_2d_pair(b_dst, &tmB, &full_bar[stage], n0, k0);
-            tma_load_2d_pair(b_dst + 8192, &tmB, &full_bar[stage], n0 + 64, k0);
+            tma_load_2d_pair(b_dst, bmap, &full_bar[stage], n0, kb0);
+            tma_load_2d_pair(b_dst + 8192, bmap, &full_bar[stage], n0 + 64, kb0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -223,6 +244,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         constexpr int CW = (EPI == 2) ? 32 : 64;   // columns per staging round (128 B per row)
         const int n0 = n_blk * P_BN;
+        const CUtensorMap* dmap = &tmD;
+        int drow0 = row0;
+        if (p.d_seg == 1) {                       // output rows belong to one of several gradient tensors
+          const int sg = (row0 >= p.off1) + (row0 >= p.off2);
+          dmap = sg == 0 ? &tmD : (sg == 1 ? &tmD2 : &tmD3);
+          drow0 = row0 - (sg == 0 ? 0 : (sg == 1 ? p.off1 : p.off2));
+        }
 #pragma unroll 1
         for (int c = 0; c < P_BN; c += CW) {
           uint8_t* stg = sStg + (n_issued & 1u) * P_STG_BYTES;
@@ -293,7 +321,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async_smem();
           named_bar(2, 128);
           if (etid == 0) {
-            tma_store_2d(&tmD, stg, col, row0);
+            tma_store_2d(dmap, stg, col, drow0);
             tma_store_commit();
           }
           ++n_issued;
@@ -317,8 +345,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const CUtensorMap& tmD,
-                       const CUtensorMap& tmD2, const CUtensorMap& tmD3, const PairParams& p, cudaStream_t stream) {
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const CUtensorMap& tmB3,
+                       const CUtensorMap& tmD, const CUtensorMap& tmD2, const CUtensorMap& tmD3, const PairParams& p,
+                       cudaStream_t stream) {
   using Cfg = PairCfg<EPI>;
   auto kern = gemm_pair_kernel<A_MN, B_MN, EPI>;
   static bool configured = false;
@@ -329,7 +358,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int tiles = p.num_m * p.num_n;
   const int max_clusters = sm_count() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  kern<<<clusters * 2, P_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB2, tmD, tmD2, tmD3, p);
+  kern<<<clusters * 2, P_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB2, tmB3, tmD, tmD2, tmD3, p);
   TN_CHECK_CUDA(cudaGetLastError());
   return TN_OK;
 }
@@ -353,12 +382,51 @@ int gemm_pair_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int6
   else       rc = encode_tmap_2d(&tmD, D, 2, uint64_t(N), uint64_t(M), uint64_t(ldd) * 2, 64, 128, true);
   if (rc) return rc;
 #define TN_PAIR(AMN_, BMN_)                                                                   \
-  (d_f32 ? launch_pair<AMN_, BMN_, 2>(tmA, tmB, tmB, tmD, tmD, tmD, p, stream)                \
-         : launch_pair<AMN_, BMN_, 0>(tmA, tmB, tmB, tmD, tmD, tmD, p, stream))
+  (d_f32 ? launch_pair<AMN_, BMN_, 2>(tmA, tmB, tmB, tmB, tmD, tmD, tmD, p, stream)           \
+         : launch_pair<AMN_, BMN_, 0>(tmA, tmB, tmB, tmB, tmD, tmD, tmD, p, stream))
   if (!a_mn && !b_mn) return TN_PAIR(false, false);
   if (!a_mn && b_mn) return TN_PAIR(false, true);
   return TN_PAIR(true, true);
 #undef TN_PAIR
+}
+
+// Three weights / gradients treated as one operand (see PairParams).  mode: 0 = forward  D[M, n0+n1+n2] = A·[B0;B1;B2]ᵀ
+// (B K-major), 1 = dgrad  D[M,N] = [A0|A1|A2]·[B0;B1;B2] (A = one [M, k0+k1+k2] buffer, B MN-major, segmented along K),
+// 2 = wgrad  [D0;D1;D2] = Aᵀ·X (A = one [Mred, m0+m1+m2] buffer MN-major, B MN-major, D segmented along M).
+int gemm_pair_seg_dispatch(int mode, const void* A, int64_t lda, const void* const* Bs, int64_t ldb, void* const* Ds,
+                           int64_t ldd, int d_f32, const int* seg, int M, int N, int K, cudaStream_t stream) {
+  PairParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
+  p.off1 = seg[0]; p.off2 = seg[0] + seg[1];
+  CUtensorMap tmA, tmB[3], tmD[3];
+  int rc;
+  if (mode == 0) {
+    p.b_seg = 1;
+    if ((rc = encode_tmap_2d(&tmA, A, 2, uint64_t(K), uint64_t(M), uint64_t(lda) * 2, 64, P_BM, true))) return rc;
+    for (int i = 0; i < 3; ++i)
+      if ((rc = encode_tmap_2d(&tmB[i], Bs[i], 2, uint64_t(K), uint64_t(seg[i]), uint64_t(ldb) * 2, 64, P_BN / 2, true))) return rc;
+    if ((rc = encode_tmap_2d(&tmD[0], Ds[0], 2, uint64_t(N), uint64_t(M), uint64_t(ldd) * 2, 64, 128, true))) return rc;
+    return launch_pair<false, false, 0>(tmA, tmB[0], tmB[1], tmB[2], tmD[0], tmD[0], tmD[0], p, stream);
+  }
+  if (mode == 1) {
+    p.b_seg = 2;
+    if ((rc = encode_tmap_2d(&tmA, A, 2, uint64_t(K), uint64_t(M), uint64_t(lda) * 2, 64, P_BM, true))) return rc;
+    for (int i = 0; i < 3; ++i)   // B_i stored [seg_i (K), N] row-major, N contiguous
+      if ((rc = encode_tmap_2d(&tmB[i], Bs[i], 2, uint64_t(N), uint64_t(seg[i]), uint64_t(ldb) * 2, 64, 64, true))) return rc;
+    if ((rc = encode_tmap_2d(&tmD[0], Ds[0], 2, uint64_t(N), uint64_t(M), uint64_t(ldd) * 2, 64, 128, true))) return rc;
+    return launch_pair<false, true, 0>(tmA, tmB[0], tmB[1], tmB[2], tmD[0], tmD[0], tmD[0], p, stream);
+  }
+  p.d_seg = 1;
+  if ((rc = encode_tmap_2d(&tmA, A, 2, uint64_t(M), uint64_t(K), uint64_t(lda) * 2, 64, 64, true))) return rc;
+  if ((rc = encode_tmap_2d(&tmB[0], Bs[0], 2, uint64_t(N), uint64_t(K), uint64_t(ldb) * 2, 64, 64, true))) return rc;
+  for (int i = 0; i < 3; ++i) {
+    if (d_f32) rc = encode_tmap_2d(&tmD[i], Ds[i], 4, uint64_t(N), uint64_t(seg[i]), uint64_t(ldd) * 4, 32, 128, true);
+    else       rc = encode_tmap_2d(&tmD[i], Ds[i], 2, uint64_t(N), uint64_t(seg[i]), uint64_t(ldd) * 2, 64, 128, true);
+    if (rc) return rc;
+  }
+  return d_f32 ? launch_pair<true, true, 2>(tmA, tmB[0], tmB[0], tmB[0], tmD[0], tmD[1], tmD[2], p, stream)
+               : launch_pair<true, true, 0>(tmA, tmB[0], tmB[0], tmB[0], tmD[0], tmD[1], tmD[2], p, stream);
 }
 
 int gemm_pair_swiglu_dispatch(const void* X, int64_t ldx, const void* Wg, const void* Wu, int64_t ldw, void* G, void* U,
@@ -374,7 +442,7 @@ int gemm_pair_swiglu_dispatch(const void* X, int64_t ldx, const void* Wg, const 
   if ((rc = encode_tmap_2d(&tmDG, G, 2, uint64_t(N), uint64_t(M), uint64_t(ldh) * 2, 64, 128, true))) return rc;
   if ((rc = encode_tmap_2d(&tmDU, U, 2, uint64_t(N), uint64_t(M), uint64_t(ldh) * 2, 64, 128, true))) return rc;
   if ((rc = encode_tmap_2d(&tmDH, H, 2, uint64_t(N), uint64_t(M), uint64_t(ldh) * 2, 64, 128, true))) return rc;
-  return launch_pair<false, false, 1>(tmA, tmG, tmU, tmDH, tmDG, tmDU, p, stream);
+  return launch_pair<false, false, 1>(tmA, tmG, tmU, tmU, tmDH, tmDG, tmDU, p, stream);
 }
 
 }  // namespace tn

@@ -86,6 +86,8 @@ int encode_tmap_3d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t d
   return encode_nd(out, ptr, elem_bytes, 3, dims, strides, box, swizzle128);
 }
 
+static int g_sm_margin = 0;
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -93,7 +95,8 @@ int sm_count() {
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
   }
-  return n;
+  const int m = n - g_sm_margin;
+  return m < 2 ? 2 : m;
 }
 
 }  // namespace tn
@@ -103,6 +106,12 @@ extern "C" {
 const char* tn_last_error(void) { return tn::g_err; }
 
 int tn_version(void) { return TOUCHNET_B200_VERSION; }
+
+int tn_set_sm_margin(int sms) {
+  if (sms < 0 || sms > 120) return tn::fail(tn::TN_ERR_ARG, "tn_set_sm_margin: %d out of range [0,120]", sms);
+  tn::g_sm_margin = sms;
+  return tn::TN_OK;
+}
 
 int tn_device_check(void) {
   int dev = 0;

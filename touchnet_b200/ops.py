@@ -115,6 +115,45 @@ def gemm_swiglu(x: torch.Tensor, wg: torch.Tensor, wu: torch.Tensor, need_gu: bo
     return g, u, h
 
 
+def qkv_fusable(M: int, nq: int, nkv: int) -> bool:
+    """The three projections run as one CTA-pair GEMM when every segment is a whole number of 256-wide tiles."""
+    return M >= 256 and nq % 256 == 0 and nkv % 256 == 0
+
+
+def gemm_qkv_fwd(x, wq, wk, wv):
+    """qkv[M, nq+2nkv] = x·[Wq;Wk;Wv]ᵀ in one launch (weights stay separate tensors)."""
+    M, K = x.shape
+    nq, nkv = wq.shape[0], wk.shape[0]
+    out = torch.empty((M, nq + 2 * nkv), dtype=BF16, device=x.device)
+    _lib.call("tn_gemm_qkv_bf16", 0, x.data_ptr(), x.stride(0), wq.data_ptr(), wk.data_ptr(), wv.data_ptr(), wq.stride(0),
+              out.data_ptr(), None, None, out.stride(0), 0, nq, nkv, nkv, M, nq + 2 * nkv, K, _st())
+    return out
+
+
+def gemm_qkv_dgrad(dqkv, wq, wk, wv):
+    """dx[M, d] = dq·Wq + dk·Wk + dv·Wv with dq|dk|dv side by side in `dqkv`."""
+    M, Kt = dqkv.shape
+    d = wq.shape[1]
+    out = torch.empty((M, d), dtype=BF16, device=dqkv.device)
+    _lib.call("tn_gemm_qkv_bf16", 1, dqkv.data_ptr(), dqkv.stride(0), wq.data_ptr(), wk.data_ptr(), wv.data_ptr(),
+              wq.stride(0), out.data_ptr(), None, None, out.stride(0), 0, wq.shape[0], wk.shape[0], wv.shape[0], M, d, Kt,
+              _st())
+    return out
+
+
+def gemm_qkv_wgrad(dqkv, x, wq, wk, wv):
+    """(dWq, dWk, dWv) = (dqᵀ·x, dkᵀ·x, dvᵀ·x) in one launch, each in its parameter's dtype."""
+    Mred, Mt = dqkv.shape
+    d = x.shape[1]
+    f32 = wq.dtype == torch.float32
+    dt = torch.float32 if f32 else BF16
+    outs = [torch.empty((w.shape[0], d), dtype=dt, device=x.device) for w in (wq, wk, wv)]
+    _lib.call("tn_gemm_qkv_bf16", 2, dqkv.data_ptr(), dqkv.stride(0), x.data_ptr(), None, None, x.stride(0),
+              outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), d, int(f32), wq.shape[0], wk.shape[0],
+              wv.shape[0], Mt, d, Mred, _st())
+    return outs
+
+
 def swiglu_bwd(g, u, dh, dg_out=None, du_out=None):
     M, N = g.shape
     dg = torch.empty_like(g) if dg_out is None else dg_out
@@ -204,11 +243,15 @@ def attn_fwd(q, k, v, plan: AttnPlan, H: int, KV: int, scale: float):
     return o, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, plan: AttnPlan, H: int, KV: int, scale: float):
+def attn_bwd(q, k, v, o, do, lse, plan: AttnPlan, H: int, KV: int, scale: float, out=None):
+    """`out` = (dq, dk, dv) preallocated (possibly strided views of one [B*T, (H+2KV)*128] buffer)."""
     B, T = plan.B, plan.T
-    dq = torch.empty((B * T, H * 128), dtype=BF16, device=q.device)
-    dk = torch.empty((B * T, KV * 128), dtype=BF16, device=q.device)
-    dv = torch.empty_like(dk)
+    if out is None:
+        dq = torch.empty((B * T, H * 128), dtype=BF16, device=q.device)
+        dk = torch.empty((B * T, KV * 128), dtype=BF16, device=q.device)
+        dv = torch.empty_like(dk)
+    else:
+        dq, dk, dv = out
     delta = torch.empty((B, H, T), dtype=torch.float32, device=q.device)
     if do.stride(1) != 1:
         do = do.contiguous()
@@ -373,7 +416,12 @@ class DecoderLayerFn(torch.autograd.Function):
         x2 = _rows2d(x)
         scale = 1.0 / math.sqrt(128)
         h1, _, rstd1 = rmsnorm_fwd(x2, ln1, eps)
-        q = gemm(h1, bf16_weight(wq)); k = gemm(h1, bf16_weight(wk)); v = gemm(h1, bf16_weight(wv))
+        nq, nkv = wq.shape[0], wk.shape[0]
+        if qkv_fusable(x2.shape[0], nq, nkv):
+            qkv = gemm_qkv_fwd(h1, bf16_weight(wq), bf16_weight(wk), bf16_weight(wv))
+            q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
+        else:
+            q = gemm(h1, bf16_weight(wq)); k = gemm(h1, bf16_weight(wk)); v = gemm(h1, bf16_weight(wv))
         if bq is not None:
             q += bq.to(BF16); k += bk.to(BF16); v += bv.to(BF16)
         rope_apply_(q, cos, sin, H, 128)
@@ -410,13 +458,24 @@ class DecoderLayerFn(torch.autograd.Function):
         # ---- attention ----
         do = gemm(dx1, bf16_weight(wo), b_mn=True)
         dwo = _wgrad(dx1, o, wo)
-        dq, dk, dv = attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale)
+        nq, nkv = wq.shape[0], wk.shape[0]
+        fused = qkv_fusable(x2.shape[0], nq, nkv) and wq.dtype == wk.dtype == wv.dtype
+        if fused:
+            dqkv = torch.empty((x2.shape[0], nq + 2 * nkv), dtype=BF16, device=x2.device)
+            dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
+            attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale, out=(dq, dk, dv))
+        else:
+            dq, dk, dv = attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale)
         rope_apply_(dq, cos, sin, H, 128, inverse=True)
         rope_apply_(dk, cos, sin, KV, 128, inverse=True)
-        dh1 = gemm(dq, bf16_weight(wq), b_mn=True)
-        dh1 = gemm(dk, bf16_weight(wk), b_mn=True, residual=dh1, out=dh1)
-        dh1 = gemm(dv, bf16_weight(wv), b_mn=True, residual=dh1, out=dh1)
-        dwq = _wgrad(dq, h1, wq); dwk = _wgrad(dk, h1, wk); dwv = _wgrad(dv, h1, wv)
+        if fused:
+            dh1 = gemm_qkv_dgrad(dqkv, bf16_weight(wq), bf16_weight(wk), bf16_weight(wv))
+            dwq, dwk, dwv = gemm_qkv_wgrad(dqkv, h1, wq, wk, wv)
+        else:
+            dh1 = gemm(dq, bf16_weight(wq), b_mn=True)
+            dh1 = gemm(dk, bf16_weight(wk), b_mn=True, residual=dh1, out=dh1)
+            dh1 = gemm(dv, bf16_weight(wv), b_mn=True, residual=dh1, out=dh1)
+            dwq = _wgrad(dq, h1, wq); dwk = _wgrad(dk, h1, wk); dwv = _wgrad(dv, h1, wv)
         dbq = dbk = dbv = None
         if ctx.has_bias:
             dbq = dq.float().sum(0).to(wq.dtype); dbk = dk.float().sum(0).to(wq.dtype); dbv = dv.float().sum(0).to(wq.dtype)

@@ -315,7 +315,7 @@ def workload_config(args, n):
                         f"stride{STRIDE} frontend on GPU, fwd+bwd, fp32 master weights + fp32 weight grads",
             "global_batch": args.batch * n, "seq_len": args.seq_len,
             "parallelism": "single GPU" if n == 1 else f"FSDP2 dp_shard={n} (bf16 params / fp32 reduce), "
-                           f"{os.environ.get('TN_SM_MARGIN', '16')} SMs left to NCCL",
+                           f"{os.environ.get('TN_SM_MARGIN', '0')} SMs left to NCCL",
             "l2_policy": "inputs larger than L2: every step streams >16 GB of weights through a 126 MB L2"}
 
 
@@ -344,7 +344,7 @@ def main():
 
     from touchnet_b200 import _lib, modeling, ops
     _lib.load()
-    sm_margin = int(os.environ.get("TN_SM_MARGIN", "16" if world > 1 else "0"))
+    sm_margin = int(os.environ.get("TN_SM_MARGIN", "0"))
     _lib.call("tn_set_sm_margin", sm_margin)   # leave SMs to the FSDP2 NCCL kernels so that they overlap the GEMMs
     B, T = args.batch, args.seq_len
     cfg = asr_config(args.layers)
@@ -378,7 +378,7 @@ def main():
 
     def one_step(inputs):
         model.zero_grad(set_to_none=True)
-        ops.invalidate_bf16_cache()          # the fp32->bf16 weight cast is part of every step
+        ops.invalidate_bf16_cache(model)     # the fp32->bf16 weight cast is part of every step
         return run_step(model, inputs, meta, B, T)
 
     # ---------------- device-resident arm ----------------

@@ -102,3 +102,26 @@ def test_embed_add_and_cast():
     assert int(flag.item()) == 1                                   # ref: :133-134 NaN check
     x = torch.randn(100003, device=dev)
     assert torch.equal(ops.cast_bf16(x), x.bfloat16())
+
+
+def test_bf16_weight_cache_follows_the_parameter_object():
+    """Regression: the bf16 working copy is cached on the parameter object (and keyed by its version counter), so a new
+    parameter that happens to reuse a freed parameter's address, or an in-place optimizer update, never sees a stale copy."""
+    dev = require_cuda()
+    w = torch.nn.Parameter(torch.randn(256, 128, device=dev))
+    a = ops.bf16_weight(w)
+    assert torch.equal(a, w.detach().bfloat16()) and ops.bf16_weight(w) is a      # cached
+    with torch.no_grad():
+        w.add_(1.0)                                                                # optimizer-style in-place update
+    b = ops.bf16_weight(w)
+    assert torch.equal(b, w.detach().bfloat16())
+    addr = w.data_ptr()
+    del w, a, b
+    w2 = torch.nn.Parameter(torch.full((256, 128), 3.0, device=dev))               # very likely the same address
+    assert torch.equal(ops.bf16_weight(w2), w2.detach().bfloat16()), (addr, w2.data_ptr())
+    m = torch.nn.Linear(128, 256, bias=False).to(dev)
+    c = ops.bf16_weight(m.weight)
+    ops.invalidate_bf16_cache(m)
+    with torch.no_grad():
+        m.weight.data.fill_(2.0)                                                   # .data writes do not bump the version
+    assert torch.equal(ops.bf16_weight(m.weight), torch.full_like(c, 2.0))

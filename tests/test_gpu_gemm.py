@@ -96,11 +96,10 @@ def test_fused_qkv_projection_forward_dgrad_wgrad(M, d, nq, nkv):
     dx = ops.gemm_qkv_dgrad(dqkv, wq, wk, wv)
     dx_ref = dqkv.float() @ torch.cat([wq, wk, wv]).float()
     assert float((dx.float() - dx_ref).abs().max()) < 1e-2 * float(dx_ref.abs().max()) + 1e-2
-    wq32, wk32, wv32 = wq.float(), wk.float(), wv.float()          # fp32 masters -> fp32 gradients
-    dws = ops.gemm_qkv_wgrad(dqkv, x, wq32, wk32, wv32)
+    dws = ops.gemm_qkv_wgrad(dqkv, x, True, nq, nkv)
     offs = [0, nq, nq + nkv, nq + 2 * nkv]
     for i, dw in enumerate(dws):
         want = dqkv[:, offs[i]:offs[i + 1]].float().t() @ x.float()
         assert dw.dtype == torch.float32 and float((dw - want).abs().max()) < 1e-4 * float(want.abs().max()) + 1e-4
-    dws_b = ops.gemm_qkv_wgrad(dqkv, x, wq, wk, wv)                 # bf16 parameters (FSDP2 mixed precision)
+    dws_b = ops.gemm_qkv_wgrad(dqkv, x, False, nq, nkv)              # bf16 parameters (FSDP2 mixed precision)
     assert all(t.dtype == torch.bfloat16 for t in dws_b)

@@ -149,7 +149,7 @@ class B200DecoderLayer(nn.Module):
 
     def forward(self, hidden_states, cos, sin, plan):
         a, m = self.self_attn, self.mlp
-        return ops.DecoderLayerFn.apply(
+        return ops.decoder_layer(
             hidden_states, self.input_layernorm.weight, a.q_proj.weight, a.k_proj.weight, a.v_proj.weight,
             a.q_proj.bias, a.k_proj.bias, a.v_proj.bias, a.o_proj.weight, self.post_attention_layernorm.weight,
             m.gate_proj.weight, m.up_proj.weight, m.down_proj.weight, cos, sin, plan, a.num_heads,

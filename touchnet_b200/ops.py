@@ -49,31 +49,30 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
-_BF16_CACHE: dict[int, tuple[int, torch.Tensor]] = {}
-
-
 def bf16_weight(w: torch.Tensor) -> torch.Tensor:
     """bf16 working copy of a parameter: the tensor itself if already bf16 (FSDP2 mixed precision hands the modules
-    bf16 unsharded parameters), else a cached cast of the fp32 master keyed on (storage address, version counter) so
-    that forward and backward of one step share a single cast."""
+    bf16 unsharded parameters), else a cast of the fp32 master cached ON THE PARAMETER OBJECT (attribute `_tn_bf16`,
+    keyed by the parameter's version counter) so that it lives and dies with the parameter and one step casts once.
+    Call it with the nn.Parameter itself (module level), not from inside an autograd Function."""
     if w.dtype == BF16:
         w = w.detach()
         return w if w.is_contiguous() else w.contiguous()
-    key, ver = w.data_ptr(), w._version
-    ent = _BF16_CACHE.get(key)
-    if ent is not None and ent[0] == ver and ent[1].shape == w.shape and ent[1].device == w.device:
+    ent = getattr(w, "_tn_bf16", None)
+    ok = ent is not None and ent[1].shape == w.shape and ent[1].device == w.device
+    if ok and ent[0] == w._version:
         return ent[1]
-    reuse = ent[1] if ent is not None and ent[1].shape == w.shape and ent[1].device == w.device else None
-    out = cast_bf16(w.detach(), reuse)
-    _BF16_CACHE[key] = (ver, out)
+    out = cast_bf16(w.detach(), ent[1] if ok else None)
+    w._tn_bf16 = (w._version, out)
     return out
 
 
-def invalidate_bf16_cache() -> None:
+def invalidate_bf16_cache(module: torch.nn.Module) -> None:
     """Force a fresh fp32->bf16 cast on next use (bench.py calls this every step: the cast is part of the step, as the
-    all-gather-time cast is under FSDP2)."""
-    for k, (ver, t) in list(_BF16_CACHE.items()):
-        _BF16_CACHE[k] = (-1, t)
+    all-gather-time cast is under FSDP2).  The buffers are kept and overwritten."""
+    for p in module.parameters():
+        ent = getattr(p, "_tn_bf16", None)
+        if ent is not None:
+            p._tn_bf16 = (-1, ent[1])
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -141,16 +140,18 @@ def gemm_qkv_dgrad(dqkv, wq, wk, wv):
     return out
 
 
-def gemm_qkv_wgrad(dqkv, x, wq, wk, wv):
-    """(dWq, dWk, dWv) = (dqᵀ·x, dkᵀ·x, dvᵀ·x) in one launch, each in its parameter's dtype."""
+def gemm_qkv_wgrad(dqkv, x, f32: bool, nq: int | None = None, nkv: int | None = None):
+    """(dWq, dWk, dWv) = (dqᵀ·x, dkᵀ·x, dvᵀ·x) in one launch; fp32 outputs for fp32 master weights, else bf16.
+    Segment sizes default to the GQA split implied by the buffer width (nq + 2*nkv) when nq is given."""
     Mred, Mt = dqkv.shape
     d = x.shape[1]
-    f32 = wq.dtype == torch.float32
+    if nq is None:
+        raise _lib.TouchNetB200Error("gemm_qkv_wgrad needs the q segment width")
+    nkv = (Mt - nq) // 2 if nkv is None else nkv
     dt = torch.float32 if f32 else BF16
-    outs = [torch.empty((w.shape[0], d), dtype=dt, device=x.device) for w in (wq, wk, wv)]
+    outs = [torch.empty((n, d), dtype=dt, device=x.device) for n in (nq, nkv, nkv)]
     _lib.call("tn_gemm_qkv_bf16", 2, dqkv.data_ptr(), dqkv.stride(0), x.data_ptr(), None, None, x.stride(0),
-              outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), d, int(f32), wq.shape[0], wk.shape[0],
-              wv.shape[0], Mt, d, Mred, _st())
+              outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), d, int(f32), nq, nkv, nkv, Mt, d, Mred, _st())
     return outs
 
 
@@ -278,26 +279,27 @@ def embed_add(input_ids: Optional[torch.Tensor], embed: Optional[torch.Tensor], 
 # ---------------------------------------------------------------------------------------------------------------
 # autograd Functions
 # ---------------------------------------------------------------------------------------------------------------
-def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, f32: bool) -> torch.Tensor:
     """dW[N,K] = dyᵀ·x, in the parameter's dtype (fp32 master -> fp32 gradient straight from the TMEM accumulator)."""
-    return gemm(dy2, x2, a_mn=True, b_mn=True, out_f32=(w.dtype == torch.float32))
+    return gemm(dy2, x2, a_mn=True, b_mn=True, out_f32=f32)
 
 
 class LinearFn(torch.autograd.Function):
     """y = x·Wᵀ (+ bias) (+ residual).  F.linear at hf:modeling_llama.py:251-289,182-184;
-    ref: touchnet/models/touch_audio/modeling_touch_audio.py:127 (projector)."""
+    ref: touchnet/models/touch_audio/modeling_touch_audio.py:127 (projector).
+    `w` is the parameter (gradient target, master dtype), `wb` its bf16 working copy (non-differentiable)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, residual):
+    def forward(ctx, x, w, wb, bias, residual):
         x2 = _rows2d(x)
         if x2.dtype != BF16:
             x2 = x2.to(BF16)
-        wb = bf16_weight(w)
         r2 = None if residual is None else _rows2d(residual)
         y = gemm(x2, wb, residual=r2)
         if bias is not None:
             y += bias.to(BF16)
-        ctx.save_for_backward(x2, w)
+        ctx.save_for_backward(x2, wb)
+        ctx.w_dtype = w.dtype
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
         ctx.x_shape = x.shape
@@ -306,24 +308,24 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w = ctx.saved_tensors
+        x2, wb = ctx.saved_tensors
         dy2 = _rows2d(dy)
         if dy2.dtype != BF16:
             dy2 = dy2.to(BF16)
         dx = dw = db = dr = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(dy2, bf16_weight(w), b_mn=True).view(ctx.x_shape).to(ctx.x_dtype)
+            dx = gemm(dy2, wb, b_mn=True).view(ctx.x_shape).to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(dy2, x2, w)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy2.float().sum(0).to(w.dtype)
-        if ctx.has_res and ctx.needs_input_grad[3]:
+            dw = gemm(dy2, x2, a_mn=True, b_mn=True, out_f32=(ctx.w_dtype == torch.float32))
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = dy2.float().sum(0).to(ctx.w_dtype)
+        if ctx.has_res and ctx.needs_input_grad[4]:
             dr = dy
-        return dx, dw, db, dr
+        return dx, dw, None, db, dr
 
 
 def linear(x, w, bias=None, residual=None):
-    return LinearFn.apply(x, w, bias, residual)
+    return LinearFn.apply(x, w, bf16_weight(w), bias, residual)
 
 
 class RMSNormFn(torch.autograd.Function):
@@ -390,76 +392,86 @@ class SwiGLUFn(torch.autograd.Function):
     """hmid = silu(x·Wgᵀ) ⊙ (x·Wuᵀ), one kernel.  hf: LlamaMLP.forward modeling_llama.py:182-184."""
 
     @staticmethod
-    def forward(ctx, x, wg, wu):
+    def forward(ctx, x, wg, wu, wgb, wub):
         x2 = _rows2d(x)
-        g, u, h = gemm_swiglu(x2, bf16_weight(wg), bf16_weight(wu))
-        ctx.save_for_backward(x2, wg, wu, g, u)
+        g, u, h = gemm_swiglu(x2, wgb, wub)
+        ctx.save_for_backward(x2, wgb, wub, g, u)
+        ctx.f32 = wg.dtype == torch.float32
         return h.view(*x.shape[:-1], wg.shape[0])
 
     @staticmethod
     def backward(ctx, dh):
-        x2, wg, wu, g, u = ctx.saved_tensors
+        x2, wgb, wub, g, u = ctx.saved_tensors
         dg, du = swiglu_bwd(g, u, _rows2d(dh))
-        dx = gemm(dg, bf16_weight(wg), b_mn=True)
-        dx = gemm(du, bf16_weight(wu), b_mn=True, residual=dx, out=dx)
-        return dx.view(*dh.shape[:-1], x2.shape[1]), _wgrad(dg, x2, wg), _wgrad(du, x2, wu)
+        dx = gemm(dg, wgb, b_mn=True)
+        dx = gemm(du, wub, b_mn=True, residual=dx, out=dx)
+        return dx.view(*dh.shape[:-1], x2.shape[1]), _wgrad(dg, x2, ctx.f32), _wgrad(du, x2, ctx.f32), None, None
+
+
+def swiglu_mlp_in(x, wg, wu):
+    return SwiGLUFn.apply(x, wg, wu, bf16_weight(wg), bf16_weight(wu))
 
 
 class DecoderLayerFn(torch.autograd.Function):
     """One pre-norm decoder block as a single autograd node (hf: LlamaDecoderLayer.forward modeling_llama.py:303-333):
-    15 kernel launches forward, residual adds fused into the o_proj / down_proj GEMM epilogues, the residual-branch
-    gradient fused into the RMSNorm backward kernel.  Parameters stay separate nn.Linear weights (HF FQNs) so FSDP2 /
-    DCP / convert_* of the reference keep working (ref: touchnet/models/helper_func.py:134-202)."""
+    12 kernel launches forward, residual adds fused into the o_proj / down_proj GEMM epilogues, q/k/v projections one
+    segmented GEMM, the residual-branch gradient fused into the RMSNorm backward kernel.  Parameters stay separate
+    nn.Linear weights (HF FQNs) so FSDP2 / DCP / convert_* of the reference keep working
+    (ref: touchnet/models/helper_func.py:134-202).  Use `decoder_layer(...)`: it resolves the bf16 working copies of the
+    fp32 master weights on the parameter objects and passes them in as non-differentiable inputs."""
 
     @staticmethod
-    def forward(ctx, x, ln1, wq, wk, wv, bq, bk, bv, wo, ln2, wg, wu, wd, cos, sin, plan, H, KV, eps):
+    def forward(ctx, x, ln1, wq, wk, wv, bq, bk, bv, wo, ln2, wg, wu, wd, wqb, wkb, wvb, wob, wgb, wub, wdb, cos, sin,
+                plan, H, KV, eps):
         x2 = _rows2d(x)
         scale = 1.0 / math.sqrt(128)
         h1, _, rstd1 = rmsnorm_fwd(x2, ln1, eps)
         nq, nkv = wq.shape[0], wk.shape[0]
         if qkv_fusable(x2.shape[0], nq, nkv):
-            qkv = gemm_qkv_fwd(h1, bf16_weight(wq), bf16_weight(wk), bf16_weight(wv))
+            qkv = gemm_qkv_fwd(h1, wqb, wkb, wvb)
             q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
         else:
-            q = gemm(h1, bf16_weight(wq)); k = gemm(h1, bf16_weight(wk)); v = gemm(h1, bf16_weight(wv))
+            q = gemm(h1, wqb); k = gemm(h1, wkb); v = gemm(h1, wvb)
         if bq is not None:
             q += bq.to(BF16); k += bk.to(BF16); v += bv.to(BF16)
         rope_apply_(q, cos, sin, H, 128)
         rope_apply_(k, cos, sin, KV, 128)
         o, lse = attn_fwd(q, k, v, plan, H, KV, scale)
-        x1 = gemm(o, bf16_weight(wo), residual=x2)
+        x1 = gemm(o, wob, residual=x2)
         h2, _, rstd2 = rmsnorm_fwd(x1, ln2, eps)
-        g, u, hm = gemm_swiglu(h2, bf16_weight(wg), bf16_weight(wu))
-        out = gemm(hm, bf16_weight(wd), residual=x1)
-        ctx.save_for_backward(x2, ln1, wq, wk, wv, wo, ln2, wg, wu, wd, cos, sin, rstd1, h1, q, k, v, o, lse, x1, rstd2,
-                              h2, g, u, hm)
+        g, u, hm = gemm_swiglu(h2, wgb, wub)
+        out = gemm(hm, wdb, residual=x1)
+        ctx.save_for_backward(x2, ln1, ln2, wqb, wkb, wvb, wob, wgb, wub, wdb, cos, sin, rstd1, h1, q, k, v, o, lse, x1,
+                              rstd2, h2, g, u, hm)
         ctx.plan, ctx.H, ctx.KV, ctx.scale, ctx.has_bias = plan, H, KV, scale, bq is not None
+        ctx.f32 = wq.dtype == torch.float32
+        ctx.w_dtype = wq.dtype
         return out.view(x.shape)
 
     @staticmethod
     def backward(ctx, dout):
-        (x2, ln1, wq, wk, wv, wo, ln2, wg, wu, wd, cos, sin, rstd1, h1, q, k, v, o, lse, x1, rstd2, h2, g, u,
+        (x2, ln1, ln2, wqb, wkb, wvb, wob, wgb, wub, wdb, cos, sin, rstd1, h1, q, k, v, o, lse, x1, rstd2, h2, g, u,
          hm) = ctx.saved_tensors
-        H, KV = ctx.H, ctx.KV
+        H, KV, f32 = ctx.H, ctx.KV, ctx.f32
         d2 = _rows2d(dout)
         if d2.dtype != BF16:
             d2 = d2.to(BF16)
         # ---- MLP ----
-        dhm = gemm(d2, bf16_weight(wd), b_mn=True)
-        dwd = _wgrad(d2, hm, wd)
+        dhm = gemm(d2, wdb, b_mn=True)
+        dwd = _wgrad(d2, hm, f32)
         dg, du = swiglu_bwd(g, u, dhm)
         del dhm
-        dh2 = gemm(dg, bf16_weight(wg), b_mn=True)
-        dh2 = gemm(du, bf16_weight(wu), b_mn=True, residual=dh2, out=dh2)
-        dwg = _wgrad(dg, h2, wg)
-        dwu = _wgrad(du, h2, wu)
+        dh2 = gemm(dg, wgb, b_mn=True)
+        dh2 = gemm(du, wub, b_mn=True, residual=dh2, out=dh2)
+        dwg = _wgrad(dg, h2, f32)
+        dwu = _wgrad(du, h2, f32)
         del dg, du
         dx1, dln2 = rmsnorm_bwd(x1, dh2, ln2, rstd2, ds_extra=d2)
         # ---- attention ----
-        do = gemm(dx1, bf16_weight(wo), b_mn=True)
-        dwo = _wgrad(dx1, o, wo)
-        nq, nkv = wq.shape[0], wk.shape[0]
-        fused = qkv_fusable(x2.shape[0], nq, nkv) and wq.dtype == wk.dtype == wv.dtype
+        do = gemm(dx1, wob, b_mn=True)
+        dwo = _wgrad(dx1, o, f32)
+        nq, nkv = wqb.shape[0], wkb.shape[0]
+        fused = qkv_fusable(x2.shape[0], nq, nkv)
         if fused:
             dqkv = torch.empty((x2.shape[0], nq + 2 * nkv), dtype=BF16, device=x2.device)
             dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
@@ -469,16 +481,22 @@ class DecoderLayerFn(torch.autograd.Function):
         rope_apply_(dq, cos, sin, H, 128, inverse=True)
         rope_apply_(dk, cos, sin, KV, 128, inverse=True)
         if fused:
-            dh1 = gemm_qkv_dgrad(dqkv, bf16_weight(wq), bf16_weight(wk), bf16_weight(wv))
-            dwq, dwk, dwv = gemm_qkv_wgrad(dqkv, h1, wq, wk, wv)
+            dh1 = gemm_qkv_dgrad(dqkv, wqb, wkb, wvb)
+            dwq, dwk, dwv = gemm_qkv_wgrad(dqkv, h1, f32, nq, nkv)
         else:
-            dh1 = gemm(dq, bf16_weight(wq), b_mn=True)
-            dh1 = gemm(dk, bf16_weight(wk), b_mn=True, residual=dh1, out=dh1)
-            dh1 = gemm(dv, bf16_weight(wv), b_mn=True, residual=dh1, out=dh1)
-            dwq = _wgrad(dq, h1, wq); dwk = _wgrad(dk, h1, wk); dwv = _wgrad(dv, h1, wv)
+            dh1 = gemm(dq, wqb, b_mn=True)
+            dh1 = gemm(dk, wkb, b_mn=True, residual=dh1, out=dh1)
+            dh1 = gemm(dv, wvb, b_mn=True, residual=dh1, out=dh1)
+            dwq = _wgrad(dq, h1, f32); dwk = _wgrad(dk, h1, f32); dwv = _wgrad(dv, h1, f32)
         dbq = dbk = dbv = None
         if ctx.has_bias:
-            dbq = dq.float().sum(0).to(wq.dtype); dbk = dk.float().sum(0).to(wq.dtype); dbv = dv.float().sum(0).to(wq.dtype)
+            dbq = dq.float().sum(0).to(ctx.w_dtype); dbk = dk.float().sum(0).to(ctx.w_dtype); dbv = dv.float().sum(0).to(ctx.w_dtype)
         dx, dln1 = rmsnorm_bwd(x2, dh1, ln1, rstd1, ds_extra=dx1)
         return (dx.view(dout.shape), dln1.to(ln1.dtype), dwq, dwk, dwv, dbq, dbk, dbv, dwo, dln2.to(ln2.dtype), dwg, dwu,
-                dwd, None, None, None, None, None, None)
+                dwd) + (None,) * 13
+
+
+def decoder_layer(x, ln1, wq, wk, wv, bq, bk, bv, wo, ln2, wg, wu, wd, cos, sin, plan, H, KV, eps):
+    return DecoderLayerFn.apply(x, ln1, wq, wk, wv, bq, bk, bv, wo, ln2, wg, wu, wd, bf16_weight(wq), bf16_weight(wk),
+                                bf16_weight(wv), bf16_weight(wo), bf16_weight(wg), bf16_weight(wu), bf16_weight(wd),
+                                cos, sin, plan, H, KV, eps)

@@ -172,6 +172,14 @@ int tn_pack_ce_fwd_bf16(const void* logits, int64_t ld, const int64_t* labels, f
 int tn_pack_ce_bwd_bf16(void* logits, int64_t ld, const int64_t* labels, const int64_t* sentence_lens, const float* lse,
                         const float* grad_scalar, float scale, int64_t M, int V, tn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * BEST-RQ tokenizer: labels of audio pre-training.  touchnet/tokenizer/tokenizer.py:289-299.
+ *   codes[t] = argmin_v || normalize(feats[t,:] @ proj) - codebook[v,:] ||_2   (lowest index on ties, like torch.argmin)
+ *   feats [T, D] fp32 (row stride ld), proj [D, E], codebook [V, E] (rows already L2-normalised, :267), E in {8,16,32}.
+ */
+int tn_bestrq_tokenize_f32(const float* feats, int64_t ld, const float* proj, const float* codebook, int64_t T, int D,
+                           int E, int V, int32_t* codes, tn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ What is executed to produce each file
                        tests/assets/config/tiny_llama.json with a dense 4-D document mask, and the reference's own
                        TouchAudioForCausalLM wrapper (per-module import) around the same text config.
   batching.npz         reference batchers batch_text / batch_pairaudio_pairtext_packed on synthetic samples.
+  bestrq.npz           reference BestRQTokenizer (random projection + nearest random code) on seeded features.
 """
 import importlib
 import json
@@ -240,8 +241,33 @@ def golden_batching():
     print("batching.npz", [k for k in out if k.endswith("attention_mask")])
 
 
+def golden_bestrq():
+    """reference BestRQTokenizer (touchnet/tokenizer/tokenizer.py:236-318) on seeded stacked-fbank-like features."""
+    import importlib
+    from types import SimpleNamespace as NS
+    tk = importlib.import_module("touchnet.tokenizer.tokenizer")
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    for tag, (D, E, V, T) in {"default": (560, 16, 8192, 128), "small": (400, 16, 1024, 129)}.items():
+        cfg = NS(tokenizer_bestrq_vocab_size=V, tokenizer_bestrq_input_size=D, tokenizer_bestrq_emb_size=E,
+                 tokenizer_bestrq_init_seed=2026, tokenizer_bestrq_init_method="default")
+        tok = tk.BestRQTokenizer(cfg)
+        feats = torch.randn(T, D, generator=g)
+        codes = tok.tokenize(feats)
+        out[f"{tag}/feats"] = feats.numpy()
+        out[f"{tag}/codes"] = np.array(codes, dtype=np.int64)
+        # the random tensors are reproducible from the seed; keep a fingerprint instead of 0.5 MB of floats
+        out[f"{tag}/quantizer_head"] = tok._quantizer.detach().numpy()[:4]
+        out[f"{tag}/codebook_head"] = tok._codebook.detach().numpy()[:4]
+        out[f"{tag}/sums"] = np.array([float(tok._quantizer.double().sum()), float(tok._codebook.double().sum())])
+        out[f"{tag}/cfg"] = np.array([D, E, V, 2026])
+    np.savez_compressed(os.path.join(HERE, "bestrq.npz"), **out)
+    print("bestrq.npz", {k: v.shape for k, v in out.items() if k.endswith("codes")})
+
+
 if __name__ == "__main__":
     functions = import_reference()
     golden_frontend(functions)
     golden_batching()
+    golden_bestrq()
     golden_model()

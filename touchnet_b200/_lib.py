@@ -41,6 +41,7 @@ _SIGNATURES = {
     "tn_feat_stack_f32": [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _vp],
     "tn_embed_add_bf16": [_vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _i64, _vp],
     "tn_cast_f32_bf16": [_vp, _vp, _i64, _vp],
+    "tn_bestrq_tokenize_f32": [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp, _vp],
     "tn_pack_ce_fwd_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _vp],
     "tn_pack_ce_bwd_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _f, _i64, _i, _vp],
 }

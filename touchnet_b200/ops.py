@@ -8,6 +8,7 @@ Reference call sites each op replaces are listed in include/touchnet_b200.h.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -114,9 +115,12 @@ def gemm_swiglu(x: torch.Tensor, wg: torch.Tensor, wu: torch.Tensor, need_gu: bo
     return g, u, h
 
 
+_FUSE_QKV = os.environ.get("TN_FUSED_QKV", "1") != "0"   # A/B switch for measurements
+
+
 def qkv_fusable(M: int, nq: int, nkv: int) -> bool:
     """The three projections run as one CTA-pair GEMM when every segment is a whole number of 256-wide tiles."""
-    return M >= 256 and nq % 256 == 0 and nkv % 256 == 0
+    return _FUSE_QKV and M >= 256 and nq % 256 == 0 and nkv % 256 == 0
 
 
 def gemm_qkv_fwd(x, wq, wk, wv):

@@ -103,6 +103,9 @@ int tn_rope_apply_bf16(void* X, int64_t ldx, const void* cos_tab, const void* si
  *   mask: allow[b,q,k] = (q >= k) && doc[b,q] == doc[b,k] && doc[b,q] > 0      (doc = attention_mask ids, int32)
  *   Q [B,T,H,128], K/V [B,T,KV,128], O [B,T,H,128] with strides (elements): token stride ld*, batch stride = T*ld*.
  *   lse [B,H,T] fp32 (natural log; +inf for fully-masked rows whose O is exactly 0).
+ *   Context parallelism (touchnet/utils/distributed.py:292-315 shards the sequence over the `cp` mesh): Tq > 0 makes
+ *   Q / O / dO / dQ / lse / delta hold only the Tq query rows starting at global position q_blk_off*128, while K / V /
+ *   dK / dV / doc_ids / meta stay global (T rows); Tq <= 0 means Tq = T, offset 0.
  *   tn_attn_prep builds, on the device with no host sync, the per-block kv/q ranges, a per-row "canonical" flag and
  *   the per-position document extents [start,end) the kernels mask with; meta: int32 buffer of tn_attn_meta_ints(B,T)
  *   elements.
@@ -111,12 +114,12 @@ int64_t tn_attn_meta_ints(int B, int T);
 int tn_attn_prep(const int32_t* doc_ids, int32_t* meta, int B, int T, tn_stream_t stream);
 int tn_attn_fwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                      int64_t ldo, float* lse, const int32_t* doc_ids, const int32_t* meta, int B, int T, int H, int KV,
-                     float scale, tn_stream_t stream);
+                     float scale, int Tq, int q_blk_off, tn_stream_t stream);
 /* backward: delta [B,H,T] fp32 workspace; dQ [B,T,H,128], dK/dV [B,T,KV,128] bf16. */
 int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, const void* O,
                      int64_t ldo, const void* dO, int64_t lddo, const float* lse, float* delta, void* dQ, int64_t lddq,
                      void* dK, int64_t lddk, void* dV, int64_t lddv, const int32_t* doc_ids, const int32_t* meta, int B,
-                     int T, int H, int KV, float scale, tn_stream_t stream);
+                     int T, int H, int KV, float scale, int Tq, int q_blk_off, tn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Audio frontend.

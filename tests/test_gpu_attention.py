@@ -153,3 +153,41 @@ def test_attention_matches_torch_flex_attention_with_hf_block_mask():
     valid = (doc > 0).reshape(-1)
     assert rel_err(o[valid].float(), o_ref[valid].float()) < 1e-2
     assert torch.all(o[~valid] == 0) and torch.all(o_ref[~valid] == 0)      # both give exact zeros on padding rows
+
+
+@pytest.mark.parametrize("T,H,KV,lens,cp", [(1024, 4, 2, [[300, 500, 100]], 2), (1024, 2, 1, [[1024]], 4),
+                                             (768, 4, 4, [[100, 50, 400, 218]], 3)])
+def test_context_parallel_query_windows(T, H, KV, lens, cp):
+    """Context parallelism shards the sequence over `cp` ranks (ref: touchnet/utils/distributed.py:292-315,
+    touchnet/bin/train.py:363-387).  Kernel-level contract, checked on one GPU: running the kernels on each rank's query
+    window (K/V global, as after the K/V all-gather) reproduces the rows of the unsharded result, and the per-window
+    dK/dV partial sums add up to the unsharded dK/dV (what the reduce-scatter computes)."""
+    dev = require_cuda()
+    B = len(lens)
+    torch.manual_seed(T + cp)
+    doc, _ = packed_doc_ids(B, T, lens, dev)
+    q = torch.randn(B, T, H * 128, device=dev).bfloat16()
+    k = torch.randn(B * T, KV * 128, device=dev).bfloat16()
+    v = torch.randn(B * T, KV * 128, device=dev).bfloat16()
+    do = torch.randn(B, T, H * 128, device=dev).bfloat16()
+    scale = 1 / math.sqrt(128)
+    full = ops.AttnPlan(doc)
+    o_full, lse_full = ops.attn_fwd(q.view(B * T, -1), k, v, full, H, KV, scale)
+    dq_full, dk_full, dv_full = ops.attn_bwd(q.view(B * T, -1), k, v, o_full, do.view(B * T, -1), lse_full, full, H, KV, scale)
+    Tq = T // cp
+    assert Tq % 128 == 0
+    dk_sum = torch.zeros_like(dk_full, dtype=torch.float32)
+    dv_sum = torch.zeros_like(dv_full, dtype=torch.float32)
+    for r in range(cp):
+        win = ops.AttnPlan(doc, Tq=Tq, q_blk_off=r * Tq // 128)
+        ql = q[:, r * Tq:(r + 1) * Tq].reshape(B * Tq, -1).contiguous()
+        dol = do[:, r * Tq:(r + 1) * Tq].reshape(B * Tq, -1).contiguous()
+        o_l, lse_l = ops.attn_fwd(ql, k, v, win, H, KV, scale)
+        ref_rows = o_full.view(B, T, -1)[:, r * Tq:(r + 1) * Tq].reshape(B * Tq, -1)
+        assert torch.equal(o_l, ref_rows)                                   # same tiles, same order: bit identical
+        assert torch.equal(lse_l, lse_full[:, :, r * Tq:(r + 1) * Tq])
+        dq_l, dk_l, dv_l = ops.attn_bwd(ql, k, v, o_l, dol, lse_l, win, H, KV, scale)
+        assert torch.equal(dq_l, dq_full.view(B, T, -1)[:, r * Tq:(r + 1) * Tq].reshape(B * Tq, -1))
+        dk_sum += dk_l.float()
+        dv_sum += dv_l.float()
+    assert rel_err(dk_sum, dk_full.float()) < 1e-2 and rel_err(dv_sum, dv_full.float()) < 1e-2

@@ -32,9 +32,9 @@ _SIGNATURES = {
     "tn_rope_apply_bf16": [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp],
     "tn_attn_meta_ints": [_i, _i],
     "tn_attn_prep": [_vp, _vp, _i, _i, _vp],
-    "tn_attn_fwd_bf16": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "tn_attn_fwd_bf16": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
     "tn_attn_bwd_bf16": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64,
-                         _vp, _i64, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+                         _vp, _i64, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
     "tn_fbank_f32": [_vp, _i, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp],
     "tn_logmel_power_f32": [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
     "tn_logmel_finish_f32": [_vp, _vp, _vp, _i, _i64, _i, _vp],

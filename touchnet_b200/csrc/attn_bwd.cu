@@ -48,6 +48,7 @@ struct AttnBwdParams {
   bf16* out2;   // dKdV: dK
   int64_t ld1, ld2;
   int B, T, H, KV, nblk;
+  int Tq, q_blk_off;   // context parallelism: Q/dO/dQ/lse/delta hold rows [q_blk_off*128, +Tq) of the global sequence
   float scale, scale_log2;
 };
 
@@ -103,14 +104,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const uint32_t warp = warp_id(), lane = lane_id();
-  const int blk = DKDV ? int(blockIdx.x) : p.nblk - 1 - int(blockIdx.x);
+  const int q_off = p.q_blk_off * ATT_BLK;                          // global position of local query row 0
+  const int nq_loc = (p.Tq + ATT_BLK - 1) / ATT_BLK;
+  const int blk_loc = DKDV ? int(blockIdx.x) : int(gridDim.x) - 1 - int(blockIdx.x);
+  const int blk = DKDV ? blk_loc : blk_loc + p.q_blk_off;           // GLOBAL block index of the resident tile
   const int hy = blockIdx.y, b = blockIdx.z;
   const int G = p.H / p.KV;
-  const int r0 = blk * ATT_BLK;  // first resident row (token position)
+  const int r0 = blk * ATT_BLK;                                     // global position of resident row 0
+  const int r0l = DKDV ? r0 : blk_loc * ATT_BLK;                    // row 0 inside the resident tensors (K/V global, Q/dO local)
+  const int res_rows = DKDV ? p.T : p.Tq;                           // rows of the resident / output tensors
+  const int s_off = DKDV ? q_off : 0;                               // streamed tensors: Q/dO are local, K/V global
   const AttnMeta meta = p.meta[b * p.nblk + blk];
-  // streamed block range and iteration count
-  const int sb_lo = DKDV ? blk : meta.kv_lo;
-  const int sb_end = DKDV ? meta.q_end : meta.kv_end;
+  // streamed block range (global block indices) and iteration count
+  const int sb_lo = DKDV ? max(blk, p.q_blk_off) : meta.kv_lo;
+  const int sb_end = DKDV ? min(meta.q_end, p.q_blk_off + nq_loc) : meta.kv_end;
   const int nsb = sb_end > sb_lo ? sb_end - sb_lo : 0;
   const int n = (DKDV ? G : 1) * nsb * 2;
 
@@ -118,8 +125,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     // no (query, key) pair touches this block: gradients are exactly zero
     for (int i = threadIdx.x; i < ATT_BLK * (ATT_HD / 8); i += BWD_THREADS) {
       const int r = i / (ATT_HD / 8), c = i % (ATT_HD / 8);
-      if (r0 + r < p.T) {
-        const int64_t tok = int64_t(b) * p.T + r0 + r;
+      if (r0l + r < res_rows) {
+        const int64_t tok = int64_t(b) * res_rows + r0l + r;
         *reinterpret_cast<uint4*>(p.out1 + tok * p.ld1 + int64_t(hy) * ATT_HD + c * 8) = make_uint4(0, 0, 0, 0);
         if (DKDV) *reinterpret_cast<uint4*>(p.out2 + tok * p.ld2 + int64_t(hy) * ATT_HD + c * 8) = make_uint4(0, 0, 0, 0);
       }
@@ -153,17 +160,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(r_full, 2 * RES_BYTES);
-      tma_load_3d(sR1, &tmR1, r_full, hy * ATT_HD, r0, b);
-      tma_load_3d(sR1 + RES_CHUNK, &tmR1, r_full, hy * ATT_HD + 64, r0, b);
-      tma_load_3d(sR2, &tmR2, r_full, hy * ATT_HD, r0, b);
-      tma_load_3d(sR2 + RES_CHUNK, &tmR2, r_full, hy * ATT_HD + 64, r0, b);
+      tma_load_3d(sR1, &tmR1, r_full, hy * ATT_HD, r0l, b);
+      tma_load_3d(sR1 + RES_CHUNK, &tmR1, r_full, hy * ATT_HD + 64, r0l, b);
+      tma_load_3d(sR2, &tmR2, r_full, hy * ATT_HD, r0l, b);
+      tma_load_3d(sR2 + RES_CHUNK, &tmR2, r_full, hy * ATT_HD + 64, r0l, b);
       for (int t = 0; t < n; ++t) {
         const int s = t % NST;
         mbar_wait(&t_empty[s], ((t / NST) & 1) ^ 1);
         mbar_arrive_expect_tx(&t_full[s], 2 * STR_BYTES);
         uint8_t* d1 = sT + s * 2 * STR_BYTES;
         uint8_t* d2 = d1 + STR_BYTES;
-        const int hs = iter_head(t), row0 = iter_row0(t);
+        const int hs = iter_head(t), row0 = iter_row0(t) - s_off;   // row inside the streamed tensor
         tma_load_3d(d1, &tmT1, &t_full[s], hs * ATT_HD, row0, b);
         tma_load_3d(d1 + STR_CHUNK, &tmT1, &t_full[s], hs * ATT_HD + 64, row0, b);
         tma_load_3d(d2, &tmT2, &t_full[s], hs * ATT_HD, row0, b);
@@ -245,9 +252,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const uint32_t sPT_u32 = smem_u32(sPT) + grp * PT_BYTES, sDST_u32 = smem_u32(sDST) + grp * PT_BYTES;
     float self_lse2 = 0.f, self_delta = 0.f;
     if (!DKDV) {
-      const int64_t idx = (int64_t(b) * p.H + hy) * p.T + self_pos;
-      self_lse2 = (self_pos < p.T) ? p.lse[idx] * 1.4426950408889634f : __int_as_float(0x7f800000);
-      self_delta = (self_pos < p.T) ? p.delta[idx] : 0.f;
+      const int lpos = self_pos - q_off;                                // local query row
+      const int64_t idx = (int64_t(b) * p.H + hy) * p.Tq + lpos;
+      self_lse2 = (lpos < p.Tq) ? p.lse[idx] * 1.4426950408889634f : __int_as_float(0x7f800000);
+      self_delta = (lpos < p.Tq) ? p.delta[idx] : 0.f;
     }
 
     // column vectors (doc ids; for dK/dV also lse, delta of the streamed q rows) are fetched one iteration ahead so
@@ -258,10 +266,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       d_out = -2; f_out = 0.f;
       if (tid < 64) {
         d_out = (pos < p.T) ? docb[pos] : -2;
-        if (DKDV) f_out = (pos < p.T) ? p.lse[(int64_t(b) * p.H + hs_) * p.T + pos] * 1.4426950408889634f
-                                      : __int_as_float(0x7f800000);
+        if (DKDV) f_out = (pos - q_off < p.Tq) ? p.lse[(int64_t(b) * p.H + hs_) * p.Tq + pos - q_off] * 1.4426950408889634f
+                                               : __int_as_float(0x7f800000);
       } else if (DKDV) {
-        f_out = (pos < p.T) ? p.delta[(int64_t(b) * p.H + hs_) * p.T + pos] : 0.f;
+        f_out = (pos - q_off < p.Tq) ? p.delta[(int64_t(b) * p.H + hs_) * p.Tq + pos - q_off] : 0.f;
       }
     };
     int32_t nxt_doc = -2; float nxt_f = 0.f;
@@ -363,8 +371,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       named_bar_sync(1 + grp, 128);
       if (tid == 0) {
         const CUtensorMap* tmo = (grp == 0) ? &tmOut1 : &tmOut2;
-        tma_store_3d(tmo, stg, hy * ATT_HD, r0, b);
-        tma_store_3d(tmo, stg + RES_CHUNK, hy * ATT_HD + 64, r0, b);
+        tma_store_3d(tmo, stg, hy * ATT_HD, r0l, b);
+        tma_store_3d(tmo, stg + RES_CHUNK, hy * ATT_HD + 64, r0l, b);
         tma_store_commit();
         tma_store_wait_read<0>();
       }
@@ -387,7 +395,7 @@ extern "C" int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64
                                 const void* O, int64_t ldo, const void* dO, int64_t lddo, const float* lse, float* delta,
                                 void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv,
                                 const int32_t* doc_ids, const int32_t* meta, int B, int T, int H, int KV, float scale,
-                                tn_stream_t stream_) {
+                                int Tq, int q_blk_off, tn_stream_t stream_) {
   clear_error();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TN_REQUIRE(Q && K && V && O && dO && lse && delta && dQ && dK && dV && doc_ids && meta, "tn_attn_bwd_bf16: null pointer");
@@ -395,32 +403,36 @@ extern "C" int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64
   TN_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 &&
                  lddk % 8 == 0 && lddv % 8 == 0, "tn_attn_bwd_bf16: strides must be multiples of 8");
   const int nblk = (T + ATT_BLK - 1) / ATT_BLK;
+  if (Tq <= 0) { Tq = T; q_blk_off = 0; }
+  TN_REQUIRE(q_blk_off >= 0 && q_blk_off * ATT_BLK + Tq <= nblk * ATT_BLK, "tn_attn_bwd_bf16: query window outside the sequence");
+  const int nqb = (Tq + ATT_BLK - 1) / ATT_BLK;
 
   {
-    const int64_t pairs = int64_t(B) * T * H;
+    const int64_t pairs = int64_t(B) * Tq * H;
     const int64_t threads = pairs * 16;
     attn_delta_kernel<<<unsigned((threads + 255) / 256), 256, 0, stream>>>(
-        static_cast<const bf16*>(O), ldo, static_cast<const bf16*>(dO), lddo, delta, B, T, H);
+        static_cast<const bf16*>(O), ldo, static_cast<const bf16*>(dO), lddo, delta, B, Tq, H);
     TN_CHECK_CUDA(cudaGetLastError());
   }
 
   CUtensorMap q128, q64, do128, do64, k128, k64, v128, v64, mdq, mdk, mdv;
   int rc;
-#define TN_MAP(m, ptr, ld, heads, box)                                                                              \
-  if ((rc = encode_tmap_3d(&m, ptr, 2, uint64_t(heads) * ATT_HD, T, B, uint64_t(ld) * 2, uint64_t(T) * (ld) * 2, 64, box, \
-                           1, true)))                                                                               \
+#define TN_MAP(m, ptr, ld, heads, box, rows)                                                                        \
+  if ((rc = encode_tmap_3d(&m, ptr, 2, uint64_t(heads) * ATT_HD, rows, B, uint64_t(ld) * 2, uint64_t(rows) * (ld) * 2, 64, \
+                           box, 1, true)))                                                                          \
     return rc;
-  TN_MAP(q128, Q, ldq, H, ATT_BLK) TN_MAP(q64, Q, ldq, H, SUB)
-  TN_MAP(do128, dO, lddo, H, ATT_BLK) TN_MAP(do64, dO, lddo, H, SUB)
-  TN_MAP(k128, K, ldk, KV, ATT_BLK) TN_MAP(k64, K, ldk, KV, SUB)
-  TN_MAP(v128, V, ldv, KV, ATT_BLK) TN_MAP(v64, V, ldv, KV, SUB)
-  TN_MAP(mdq, dQ, lddq, H, ATT_BLK) TN_MAP(mdk, dK, lddk, KV, ATT_BLK) TN_MAP(mdv, dV, lddv, KV, ATT_BLK)
+  TN_MAP(q128, Q, ldq, H, ATT_BLK, Tq) TN_MAP(q64, Q, ldq, H, SUB, Tq)
+  TN_MAP(do128, dO, lddo, H, ATT_BLK, Tq) TN_MAP(do64, dO, lddo, H, SUB, Tq)
+  TN_MAP(k128, K, ldk, KV, ATT_BLK, T) TN_MAP(k64, K, ldk, KV, SUB, T)
+  TN_MAP(v128, V, ldv, KV, ATT_BLK, T) TN_MAP(v64, V, ldv, KV, SUB, T)
+  TN_MAP(mdq, dQ, lddq, H, ATT_BLK, Tq) TN_MAP(mdk, dK, lddk, KV, ATT_BLK, T) TN_MAP(mdv, dV, lddv, KV, ATT_BLK, T)
 #undef TN_MAP
 
   AttnBwdParams p{};
   p.doc = doc_ids; p.meta = reinterpret_cast<const AttnMeta*>(meta); p.lse = lse; p.delta = delta;
   p.seg = reinterpret_cast<const AttnSeg*>(meta + attn_meta_seg_off(B, nblk));
   p.B = B; p.T = T; p.H = H; p.KV = KV; p.nblk = nblk;
+  p.Tq = Tq; p.q_blk_off = q_blk_off;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
 
   static bool configured = false;
@@ -438,7 +450,7 @@ extern "C" int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64
   {
     AttnBwdParams pq = p;
     pq.out1 = static_cast<bf16*>(dQ); pq.ld1 = lddq; pq.out2 = nullptr; pq.ld2 = 0;
-    attn_bwd_kernel<false><<<dim3(nblk, H, B), BWD_THREADS, BwdSmem::ALLOC, stream>>>(q128, do128, k64, v64, mdq, mdq, pq);
+    attn_bwd_kernel<false><<<dim3(nqb, H, B), BWD_THREADS, BwdSmem::ALLOC, stream>>>(q128, do128, k64, v64, mdq, mdq, pq);
     TN_CHECK_CUDA(cudaGetLastError());
   }
   return TN_OK;

@@ -221,6 +221,8 @@ struct AttnFwdParams {
   bf16* O;       // for the all-padding fast path
   int64_t ldo;
   int B, T, H, KV, nblk;
+  int Tq, q_blk_off;  // context parallelism: the Q/O/lse tensors hold rows [q_blk_off*128, q_blk_off*128 + Tq) of the
+                      // global sequence of length T; K/V/doc/meta are global.  Tq == T, off == 0 without CP.
   float scale_log2;  // softmax scale * log2(e)
 };
 
@@ -247,10 +249,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const uint32_t warp = warp_id(), lane = lane_id();
-  const int qb = p.nblk - 1 - int(blockIdx.x);  // heaviest (latest) q blocks first
+  const int qb_loc = int(gridDim.x) - 1 - int(blockIdx.x);  // heaviest (latest) q blocks first
+  const int qb = qb_loc + p.q_blk_off;                      // global block index (meta / doc / seg / masking)
   const int h = blockIdx.y, b = blockIdx.z;
   const int kvh = h / (p.H / p.KV);
-  const int q0 = qb * ATT_BLK;
+  const int q0 = qb * ATT_BLK;          // global position of row 0
+  const int q0l = qb_loc * ATT_BLK;     // row 0 inside the (local) Q / O / lse tensors
   const AttnMeta meta = p.meta[b * p.nblk + qb];
   const int kv_lo = meta.kv_lo;
   const int n = meta.kv_end - meta.kv_lo;
@@ -260,12 +264,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int tid = threadIdx.x;
     for (int i = tid; i < ATT_BLK * (ATT_HD / 8); i += FWD_THREADS) {
       const int r = i / (ATT_HD / 8), c = i % (ATT_HD / 8);
-      if (q0 + r < p.T)
-        *reinterpret_cast<uint4*>(p.O + (int64_t(b) * p.T + q0 + r) * p.ldo + int64_t(h) * ATT_HD + c * 8) =
+      if (q0l + r < p.Tq)
+        *reinterpret_cast<uint4*>(p.O + (int64_t(b) * p.Tq + q0l + r) * p.ldo + int64_t(h) * ATT_HD + c * 8) =
             make_uint4(0, 0, 0, 0);
     }
     for (int r = tid; r < ATT_BLK; r += FWD_THREADS)
-      if (q0 + r < p.T) p.lse[(int64_t(b) * p.H + h) * p.T + q0 + r] = __int_as_float(0x7f800000);
+      if (q0l + r < p.Tq) p.lse[(int64_t(b) * p.H + h) * p.Tq + q0l + r] = __int_as_float(0x7f800000);
     return;
   }
 
@@ -295,8 +299,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, h * ATT_HD, q0, b, kEvictFirst);
-      tma_load_3d(sQ + CHUNK_BYTES, &tmQ, q_full, h * ATT_HD + 64, q0, b, kEvictFirst);
+      tma_load_3d(sQ, &tmQ, q_full, h * ATT_HD, q0l, b, kEvictFirst);
+      tma_load_3d(sQ + CHUNK_BYTES, &tmQ, q_full, h * ATT_HD + 64, q0l, b, kEvictFirst);
       for (int j = 0; j < n; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
@@ -501,14 +505,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         sts_u4(sP_u32 + (col >> 6) * CHUNK_BYTES + sw128_off(r, (col & 63) >> 3), make_uint4(w[0], w[1], w[2], w[3]));
       }
     }
-    if (qpos < p.T)
-      p.lse[(int64_t(b) * p.H + h) * p.T + qpos] =
+    if (q0l + int(r) < p.Tq)
+      p.lse[(int64_t(b) * p.H + h) * p.Tq + q0l + int(r)] =
           (l_run > 0.f) ? (m_run + log2f(l_run)) * 0.6931471805599453f : __int_as_float(0x7f800000);
     fence_proxy_async_smem();
     named_bar_sync(1, 128);
     if (tid == 0) {
-      tma_store_3d(&tmO, sP, h * ATT_HD, q0, b);
-      tma_store_3d(&tmO, sP + CHUNK_BYTES, h * ATT_HD + 64, q0, b);
+      tma_store_3d(&tmO, sP, h * ATT_HD, q0l, b);
+      tma_store_3d(&tmO, sP + CHUNK_BYTES, h * ATT_HD + 64, q0l, b);
       tma_store_commit();
       tma_store_wait_read<0>();
     }
@@ -548,7 +552,7 @@ extern "C" int tn_attn_prep(const int32_t* doc_ids, int32_t* meta, int B, int T,
 
 extern "C" int tn_attn_fwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
                                 void* O, int64_t ldo, float* lse, const int32_t* doc_ids, const int32_t* meta, int B,
-                                int T, int H, int KV, float scale, tn_stream_t stream_) {
+                                int T, int H, int KV, float scale, int Tq, int q_blk_off, tn_stream_t stream_) {
   clear_error();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TN_REQUIRE(Q && K && V && O && lse && doc_ids && meta, "tn_attn_fwd_bf16: null pointer");
@@ -557,24 +561,28 @@ extern "C" int tn_attn_fwd_bf16(const void* Q, int64_t ldq, const void* K, int64
   TN_REQUIRE(ldq >= int64_t(H) * ATT_HD && ldo >= int64_t(H) * ATT_HD && ldk >= int64_t(KV) * ATT_HD &&
                  ldv >= int64_t(KV) * ATT_HD, "tn_attn_fwd_bf16: token stride smaller than heads*128");
   const int nblk = (T + ATT_BLK - 1) / ATT_BLK;
+  if (Tq <= 0) { Tq = T; q_blk_off = 0; }
+  TN_REQUIRE(q_blk_off >= 0 && q_blk_off * ATT_BLK + Tq <= nblk * ATT_BLK, "tn_attn_fwd_bf16: query window outside the sequence");
+  const int nqb = (Tq + ATT_BLK - 1) / ATT_BLK;
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
-  if ((rc = encode_tmap_3d(&tmQ, Q, 2, uint64_t(H) * ATT_HD, T, B, ldq * 2, uint64_t(T) * ldq * 2, 64, ATT_BLK, 1, true))) return rc;
+  if ((rc = encode_tmap_3d(&tmQ, Q, 2, uint64_t(H) * ATT_HD, Tq, B, ldq * 2, uint64_t(Tq) * ldq * 2, 64, ATT_BLK, 1, true))) return rc;
   if ((rc = encode_tmap_3d(&tmK, K, 2, uint64_t(KV) * ATT_HD, T, B, ldk * 2, uint64_t(T) * ldk * 2, 64, ATT_BLK, 1, true))) return rc;
   if ((rc = encode_tmap_3d(&tmV, V, 2, uint64_t(KV) * ATT_HD, T, B, ldv * 2, uint64_t(T) * ldv * 2, 64, ATT_BLK, 1, true))) return rc;
-  if ((rc = encode_tmap_3d(&tmO, O, 2, uint64_t(H) * ATT_HD, T, B, ldo * 2, uint64_t(T) * ldo * 2, 64, ATT_BLK, 1, true))) return rc;
+  if ((rc = encode_tmap_3d(&tmO, O, 2, uint64_t(H) * ATT_HD, Tq, B, ldo * 2, uint64_t(Tq) * ldo * 2, 64, ATT_BLK, 1, true))) return rc;
   AttnFwdParams p{};
   p.doc = doc_ids; p.meta = reinterpret_cast<const AttnMeta*>(meta); p.lse = lse;
   p.seg = reinterpret_cast<const AttnSeg*>(meta + attn_meta_seg_off(B, nblk));
   p.O = static_cast<bf16*>(O); p.ldo = ldo;
   p.B = B; p.T = T; p.H = H; p.KV = KV; p.nblk = nblk;
+  p.Tq = Tq; p.q_blk_off = q_blk_off;
   p.scale_log2 = scale * 1.4426950408889634f;
   static bool configured = false;
   if (!configured) {
     TN_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::ALLOC));
     configured = true;
   }
-  dim3 grid(nblk, H, B);
+  dim3 grid(nqb, H, B);
   attn_fwd_kernel<<<grid, FWD_THREADS, FwdSmem::ALLOC, stream>>>(tmQ, tmK, tmV, tmO, p);
   TN_CHECK_CUDA(cudaGetLastError());
   return TN_OK;

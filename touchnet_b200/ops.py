@@ -227,10 +227,15 @@ def rope_apply_(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: 
 class AttnPlan:
     """Per-step packing metadata shared by every layer: int32 document ids + per-block kv/q ranges, built on device."""
 
-    def __init__(self, doc_ids: torch.Tensor):
+    def __init__(self, doc_ids: torch.Tensor, Tq: Optional[int] = None, q_blk_off: int = 0):
+        """doc_ids: GLOBAL [B,T] document ids.  Tq / q_blk_off: context-parallel query window (rows
+        [q_blk_off*128, q_blk_off*128 + Tq) of the sequence live on this rank); default = the whole sequence."""
         _chk(doc_ids, "attention_mask (document ids)")
         assert doc_ids.dim() == 2
         self.B, self.T = doc_ids.shape
+        self.Tq = self.T if Tq is None else int(Tq)
+        self.q_blk_off = int(q_blk_off)
+        self.cp_group = None
         self.doc = doc_ids.to(torch.int32).contiguous()
         n_ints = int(_lib.load().tn_attn_meta_ints(self.B, self.T))
         self.meta = torch.empty(n_ints, dtype=torch.int32, device=doc_ids.device)
@@ -238,32 +243,35 @@ class AttnPlan:
 
 
 def attn_fwd(q, k, v, plan: AttnPlan, H: int, KV: int, scale: float):
-    """q [B*T, H*128], k/v [B*T, KV*128] (row strides arbitrary) -> o [B*T, H*128], lse [B,H,T]."""
+    """q [B*Tq, H*128], k/v [B*T, KV*128] (row strides arbitrary) -> o [B*Tq, H*128], lse [B,H,Tq].
+    Tq == T unless the plan describes a context-parallel query window (plan.Tq, plan.q_blk_off)."""
     B, T = plan.B, plan.T
-    o = torch.empty((B * T, H * 128), dtype=BF16, device=q.device)
-    lse = torch.empty((B, H, T), dtype=torch.float32, device=q.device)
+    Tq = plan.Tq
+    o = torch.empty((B * Tq, H * 128), dtype=BF16, device=q.device)
+    lse = torch.empty((B, H, Tq), dtype=torch.float32, device=q.device)
     _lib.call("tn_attn_fwd_bf16", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
               o.data_ptr(), o.stride(0), lse.data_ptr(), plan.doc.data_ptr(), plan.meta.data_ptr(), B, T, H, KV,
-              float(scale), _st())
+              float(scale), Tq, plan.q_blk_off, _st())
     return o, lse
 
 
 def attn_bwd(q, k, v, o, do, lse, plan: AttnPlan, H: int, KV: int, scale: float, out=None):
     """`out` = (dq, dk, dv) preallocated (possibly strided views of one [B*T, (H+2KV)*128] buffer)."""
     B, T = plan.B, plan.T
+    Tq = plan.Tq
     if out is None:
-        dq = torch.empty((B * T, H * 128), dtype=BF16, device=q.device)
+        dq = torch.empty((B * Tq, H * 128), dtype=BF16, device=q.device)
         dk = torch.empty((B * T, KV * 128), dtype=BF16, device=q.device)
         dv = torch.empty_like(dk)
     else:
         dq, dk, dv = out
-    delta = torch.empty((B, H, T), dtype=torch.float32, device=q.device)
+    delta = torch.empty((B, H, Tq), dtype=torch.float32, device=q.device)
     if do.stride(1) != 1:
         do = do.contiguous()
     _lib.call("tn_attn_bwd_bf16", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
               o.data_ptr(), o.stride(0), do.data_ptr(), do.stride(0), lse.data_ptr(), delta.data_ptr(),
               dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0),
-              plan.doc.data_ptr(), plan.meta.data_ptr(), B, T, H, KV, float(scale), _st())
+              plan.doc.data_ptr(), plan.meta.data_ptr(), B, T, H, KV, float(scale), Tq, plan.q_blk_off, _st())
     return dq, dk, dv
 
 

@@ -76,3 +76,13 @@ def cp_attn_bwd(q, kf, vf, o, do, lse, plan: ops.AttnPlan, H: int, KV: int, scal
     dk = _reduce_scatter_seq(dk_full, plan.B, plan.cp_group)
     dv = _reduce_scatter_seq(dv_full, plan.B, plan.cp_group)
     return dq, dk, dv
+
+
+def enable_context_parallel(model: torch.nn.Module, group: Optional[dist.ProcessGroup]) -> None:
+    """Mark a B200LlamaForCausalLM / B200TouchAudioForCausalLM as running on sequence shards of the given cp group
+    (pass None to switch it off).  The caller feeds every per-token buffer already sharded on dim 1, as the reference's
+    `create_context_parallel_ctx` does (ref: touchnet/bin/train.py:363-387)."""
+    from . import modeling
+    for m in model.modules():
+        if isinstance(m, modeling.B200LlamaModel):
+            m.cp_group = group

@@ -177,12 +177,19 @@ class B200LlamaModel(nn.Module):
         B, T, _ = inputs_embeds.shape
         dev = inputs_embeds.device
         if position_ids is None:
+            if getattr(self, "cp_group", None) is not None:
+                raise TouchNetB200Error("context parallelism needs the (sharded) position_ids of the packed batch")
             position_ids = torch.arange(T, device=dev, dtype=torch.int64)[None].expand(B, T)
         if attention_mask is None:
             attention_mask = torch.ones((B, T), dtype=torch.int32, device=dev)
         if attention_mask.dim() != 2:
             raise TouchNetB200Error("attention_mask must be the [B,T] document-id tensor of the packed batch")
-        plan = ops.AttnPlan(attention_mask)                 # once per step, shared by all layers
+        cp_group = getattr(self, "cp_group", None)
+        if cp_group is not None:                            # sequence sharded over the cp mesh: see context_parallel.py
+            from . import context_parallel
+            plan = context_parallel.make_cp_plan(attention_mask, cp_group)
+        else:
+            plan = ops.AttnPlan(attention_mask)             # once per step, shared by all layers
         cos, sin = self.rotary_emb(position_ids)            # once per step
         x = inputs_embeds
         if x.dtype != torch.bfloat16:

@@ -448,7 +448,11 @@ class DecoderLayerFn(torch.autograd.Function):
             q += bq.to(BF16); k += bk.to(BF16); v += bv.to(BF16)
         rope_apply_(q, cos, sin, H, 128)
         rope_apply_(k, cos, sin, KV, 128)
-        o, lse = attn_fwd(q, k, v, plan, H, KV, scale)
+        if plan.cp_group is None:
+            o, lse = attn_fwd(q, k, v, plan, H, KV, scale)
+        else:   # context parallel: K/V of all cp ranks are gathered, the kernel runs on this rank's query window
+            from . import context_parallel as _cp
+            o, lse, k, v = _cp.cp_attn_fwd(q, k, v, plan, H, KV, scale)
         x1 = gemm(o, wob, residual=x2)
         h2, _, rstd2 = rmsnorm_fwd(x1, ln2, eps)
         g, u, hm = gemm_swiglu(h2, wgb, wub)
@@ -484,7 +488,13 @@ class DecoderLayerFn(torch.autograd.Function):
         dwo = _wgrad(dx1, o, f32)
         nq, nkv = wqb.shape[0], wkb.shape[0]
         fused = qkv_fusable(x2.shape[0], nq, nkv)
-        if fused:
+        if ctx.plan.cp_group is not None:
+            from . import context_parallel as _cp
+            dq, dk, dv = _cp.cp_attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale)   # dK/dV reduce-scattered
+            if fused:
+                dqkv = torch.cat([dq, dk, dv], dim=1)
+                dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
+        elif fused:
             dqkv = torch.empty((x2.shape[0], nq + 2 * nkv), dtype=BF16, device=x2.device)
             dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
             attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale, out=(dq, dk, dv))

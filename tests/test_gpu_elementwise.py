@@ -125,3 +125,9 @@ def test_bf16_weight_cache_follows_the_parameter_object():
     with torch.no_grad():
         m.weight.data.fill_(2.0)                                                   # .data writes do not bump the version
     assert torch.equal(ops.bf16_weight(m.weight), torch.full_like(c, 2.0))
+    # side-stream prefetch: same values, consumer waits on the per-parameter event
+    ops.invalidate_bf16_cache(m)
+    with torch.no_grad():
+        m.weight.data.fill_(5.0)
+    assert ops.prefetch_bf16_weights(m) == 1 and ops.prefetch_bf16_weights(m) == 0
+    assert torch.equal(ops.bf16_weight(m.weight), torch.full_like(c, 5.0))

@@ -52,18 +52,23 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
 
 def bf16_weight(w: torch.Tensor) -> torch.Tensor:
     """bf16 working copy of a parameter: the tensor itself if already bf16 (FSDP2 mixed precision hands the modules
-    bf16 unsharded parameters), else a cast of the fp32 master cached ON THE PARAMETER OBJECT (attribute `_tn_bf16`,
-    keyed by the parameter's version counter) so that it lives and dies with the parameter and one step casts once.
-    Call it with the nn.Parameter itself (module level), not from inside an autograd Function."""
+    bf16 unsharded parameters), else a cast of the fp32 master cached ON THE PARAMETER OBJECT (attribute `_tn_bf16` =
+    (version, tensor, event), keyed by the parameter's version counter) so that it lives and dies with the parameter and
+    one step casts once.  Call it with the nn.Parameter itself (module level), not from inside an autograd Function.
+    If the copy was produced ahead of time on the side stream (`prefetch_bf16_weights`), the current stream is made to
+    wait for it here."""
     if w.dtype == BF16:
         w = w.detach()
         return w if w.is_contiguous() else w.contiguous()
     ent = getattr(w, "_tn_bf16", None)
     ok = ent is not None and ent[1].shape == w.shape and ent[1].device == w.device
     if ok and ent[0] == w._version:
+        if ent[2] is not None:
+            torch.cuda.current_stream().wait_event(ent[2])
+            w._tn_bf16 = (ent[0], ent[1], None)
         return ent[1]
     out = cast_bf16(w.detach(), ent[1] if ok else None)
-    w._tn_bf16 = (w._version, out)
+    w._tn_bf16 = (w._version, out, None)
     return out
 
 
@@ -73,7 +78,45 @@ def invalidate_bf16_cache(module: torch.nn.Module) -> None:
     for p in module.parameters():
         ent = getattr(p, "_tn_bf16", None)
         if ent is not None:
-            p._tn_bf16 = (-1, ent[1])
+            p._tn_bf16 = (-1, ent[1], None)
+
+
+_CAST_STREAM: dict = {}
+
+
+def prefetch_bf16_weights(module: torch.nn.Module) -> int:
+    """Issue the fp32->bf16 casts of every stale >=2-D fp32 parameter of `module` on a side stream, in parameter order,
+    so that these HBM-bound copies overlap the tensor-bound GEMMs of the layers in front of them (the same idea as
+    FSDP2's all-gather prefetch).  Consumers synchronise per parameter through an event (see bf16_weight).
+    Returns the number of casts issued."""
+    params, seen = [], set()
+    for m in module.modules():          # nn.Linear weights are the only tensors consumed through bf16_weight()
+        w = getattr(m, "weight", None) if isinstance(m, torch.nn.Linear) else None
+        if w is not None and w.dtype == torch.float32 and w.is_cuda and id(w) not in seen:
+            seen.add(id(w))
+            params.append(w)
+    todo = []
+    for p in params:
+        ent = getattr(p, "_tn_bf16", None)
+        ok = ent is not None and ent[1].shape == p.shape and ent[1].device == p.device
+        if not (ok and ent[0] == p._version):
+            todo.append((p, ent[1] if ok else None))
+    if not todo:
+        return 0
+    dev = todo[0][0].device
+    side = _CAST_STREAM.get(dev)
+    if side is None:
+        side = _CAST_STREAM[dev] = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream(dev)
+    side.wait_stream(cur)          # everything that still reads the old copies (or writes the masters) is ahead of us
+    with torch.cuda.stream(side):
+        for p, buf in todo:
+            out = cast_bf16(p.detach(), buf)
+            out.record_stream(cur)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            p._tn_bf16 = (p._version, out, ev)
+    return len(todo)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -216,6 +216,17 @@ def attn_flops_fwd_per_layer(doc_lens, H=32, hd=128):
     return 4.0 * H * hd * sum(n * (n + 1) / 2 for n in doc_lens)
 
 
+def gemm_traffic():
+    """Average DRAM bytes per GEMM launch of the step, from the committed ncu capture (profiles/r01_gemm_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -441,8 +452,10 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": gemm_tflops / peaks["bf16_sustained"], "traffic": None,
-                     "kernel": "tn::gemm_kernel<BN,A_MN,B_MN,EPI> (all GEMM launches of the timed region)",
+                     "frac": gemm_tflops / peaks["bf16_sustained"],
+                     "traffic": (gemm_traffic() or {}).get("avg_dram_bytes_per_gemm_launch"),
+                     "algorithmic_bytes_per_launch": (gemm_traffic() or {}).get("avg_algorithmic_bytes_per_gemm_launch"),
+                     "kernel": "tn::gemm_pair_kernel<A_MN,B_MN,EPI> (all GEMM launches of the timed region)",
                      "launches": gemm_n, "share_of_step": gemm_ms / ms if ms > 0 else None,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); burst {peaks['bf16_burst']}"},
         "extras": {"nonpad_tokens_per_step_rank0": meta["nonpad_tokens"], "docs_rank0": len(meta["doc_lens"]),

@@ -58,10 +58,12 @@ int tn_gemm_swiglu_bf16(const void* X, int64_t ldx, const void* Wg, const void* 
  *   mode 0 forward  D0[M, s0+s1+s2] = A[M,K] · [B0;B1;B2]ᵀ         (B_i [s_i, K]; q|k|v land side by side in one buffer)
  *   mode 1 dgrad    D0[M, N]        = A[M, s0+s1+s2] · [B0;B1;B2]   (A = dq|dk|dv side by side; B_i [s_i, N])
  *   mode 2 wgrad    D_i[s_i, N]     = A[:, seg_i]ᵀ · B0[Mred=K, N]  (A = dq|dk|dv [K, s0+s1+s2]; B0 = layer input x)
- * Segment sizes must be multiples of 256.  hf:models/llama/modeling_llama.py:251-289 (q_proj, k_proj, v_proj). */
+ * Segment sizes must be multiples of 256.  hf:models/llama/modeling_llama.py:251-289 (q_proj, k_proj, v_proj).
+ * mode 0 with rope_cos/rope_sin ([M, 64] bf16 tables of tn_rope_table): the epilogue also applies RoPE to the q and k
+ * segments (hf apply_rotary_pos_emb :151-168) with the rounding points of the unfused bf16 ops (bit-identical). */
 int tn_gemm_qkv_bf16(int mode, const void* A, int64_t lda, const void* B0, const void* B1, const void* B2, int64_t ldb,
                      void* D0, void* D1, void* D2, int64_t ldd, int d_f32, int s0, int s1, int s2, int M, int N, int K,
-                     tn_stream_t stream);
+                     const void* rope_cos, const void* rope_sin, tn_stream_t stream);
 
 /* SwiGLU backward (elementwise): dG = dH⊙U⊙silu'(G), dU = dH⊙silu(G).  bf16 [M,N] contiguous rows (ld). */
 int tn_swiglu_bwd_bf16(const void* G, const void* U, const void* dH, void* dG, void* dU, int64_t rows, int64_t cols,
@@ -115,11 +117,14 @@ int tn_attn_prep(const int32_t* doc_ids, int32_t* meta, int B, int T, tn_stream_
 int tn_attn_fwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
                      int64_t ldo, float* lse, const int32_t* doc_ids, const int32_t* meta, int B, int T, int H, int KV,
                      float scale, int Tq, int q_blk_off, tn_stream_t stream);
-/* backward: delta [B,H,T] fp32 workspace; dQ [B,T,H,128], dK/dV [B,T,KV,128] bf16. */
+/* backward: delta [B,H,T] fp32 workspace; dQ [B,T,H,128], dK/dV [B,T,KV,128] bf16.  Optional fused inverse RoPE: with
+ * rope_cos_q/sin_q ([B*Tq, 64] bf16 tables of tn_rope_table) dQ is returned w.r.t. the UN-rotated q, likewise
+ * rope_cos_k/sin_k ([B*T, 64]) for dK (backward of hf apply_rotary_pos_emb, modeling_llama.py:151-168); NULL = off. */
 int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, const void* O,
                      int64_t ldo, const void* dO, int64_t lddo, const float* lse, float* delta, void* dQ, int64_t lddq,
                      void* dK, int64_t lddk, void* dV, int64_t lddv, const int32_t* doc_ids, const int32_t* meta, int B,
-                     int T, int H, int KV, float scale, int Tq, int q_blk_off, tn_stream_t stream);
+                     int T, int H, int KV, float scale, int Tq, int q_blk_off, const void* rope_cos_q,
+                     const void* rope_sin_q, const void* rope_cos_k, const void* rope_sin_k, tn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Audio frontend.

@@ -191,3 +191,27 @@ def test_context_parallel_query_windows(T, H, KV, lens, cp):
         dk_sum += dk_l.float()
         dv_sum += dv_l.float()
     assert rel_err(dk_sum, dk_full.float()) < 1e-2 and rel_err(dv_sum, dv_full.float()) < 1e-2
+
+
+def test_backward_fused_inverse_rope_matches_separate_kernel():
+    """dQ/dK with the inverse RoPE applied in the attention-backward epilogue (fp32, one rounding) vs the separate
+    in-place kernel on the bf16 gradients (several roundings): equal within bf16 noise; dV untouched."""
+    dev = require_cuda()
+    B, T, H, KV = 2, 384, 4, 2
+    doc, pos = packed_doc_ids(B, T, [[100, 200, 50], [384]], dev)
+    inv, sc = mo.rope_inv_freq(mo.OracleConfig(512, 8, 1, H, KV, 128, 8, rope_theta=10000.0))
+    cos, sin = ops.rope_table(pos, inv.to(dev), sc)
+    torch.manual_seed(9)
+    q = torch.randn(B * T, H * 128, device=dev).bfloat16()
+    k = torch.randn(B * T, KV * 128, device=dev).bfloat16()
+    v = torch.randn(B * T, KV * 128, device=dev).bfloat16()
+    do = torch.randn(B * T, H * 128, device=dev).bfloat16()
+    plan = ops.AttnPlan(doc)
+    scale = 1 / math.sqrt(128)
+    o, lse = ops.attn_fwd(q, k, v, plan, H, KV, scale)
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, plan, H, KV, scale)
+    ops.rope_apply_(dq, cos, sin, H, 128, inverse=True)
+    ops.rope_apply_(dk, cos, sin, KV, 128, inverse=True)
+    dq_f, dk_f, dv_f = ops.attn_bwd(q, k, v, o, do, lse, plan, H, KV, scale, rope=(cos, sin))
+    assert torch.equal(dv_f, dv)
+    assert rel_err(dq_f.float(), dq.float()) < 1e-2 and rel_err(dk_f.float(), dk.float()) < 1e-2

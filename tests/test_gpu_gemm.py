@@ -103,3 +103,24 @@ def test_fused_qkv_projection_forward_dgrad_wgrad(M, d, nq, nkv):
         assert dw.dtype == torch.float32 and float((dw - want).abs().max()) < 1e-4 * float(want.abs().max()) + 1e-4
     dws_b = ops.gemm_qkv_wgrad(dqkv, x, False, nq, nkv)              # bf16 parameters (FSDP2 mixed precision)
     assert all(t.dtype == torch.bfloat16 for t in dws_b)
+
+
+@pytest.mark.parametrize("M,d,H,KV", [(512, 512, 4, 2), (8192, 4096, 32, 8), (300, 1024, 2, 2)])
+def test_fused_qkv_rope_epilogue_is_bit_identical_to_unfused(M, d, H, KV):
+    """RoPE in the QKV GEMM epilogue == GEMM followed by the in-place RoPE kernel (same bf16 rounding points)."""
+    dev = require_cuda()
+    from oracle import model_oracle as mo
+    torch.manual_seed(M)
+    nq, nkv = H * 128, KV * 128
+    x = (torch.randn(M, d, device=dev) * 0.5).bfloat16()
+    wq = (torch.randn(nq, d, device=dev) * 0.05).bfloat16()
+    wk = (torch.randn(nkv, d, device=dev) * 0.05).bfloat16()
+    wv = (torch.randn(nkv, d, device=dev) * 0.05).bfloat16()
+    pos = (torch.arange(M, device=dev) % 700)[None]
+    inv, sc = mo.rope_inv_freq(mo.OracleConfig(d, 8, 1, H, KV, 128, 8, rope_theta=500000.0))
+    cos, sin = ops.rope_table(pos, inv.to(dev), sc)
+    fused = ops.gemm_qkv_fwd(x, wq, wk, wv, rope=(cos, sin))
+    plain = ops.gemm_qkv_fwd(x, wq, wk, wv)
+    ops.rope_apply_(plain[:, :nq], cos, sin, H, 128)
+    ops.rope_apply_(plain[:, nq:nq + nkv], cos, sin, KV, 128)
+    assert torch.equal(fused, plain)

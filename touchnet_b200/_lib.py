@@ -23,7 +23,8 @@ _SIGNATURES = {
     "tn_set_sm_margin": [_i],
     "tn_gemm_bf16": [_vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _vp],
     "tn_gemm_swiglu_bf16": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
-    "tn_gemm_qkv_bf16": [_i, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "tn_gemm_qkv_bf16": [_i, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp,
+                         _vp],
     "tn_swiglu_bwd_bf16": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     "tn_rmsnorm_fwd_bf16": [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _f, _vp],
     "tn_rmsnorm_bwd_bf16": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i64, _i, _vp],
@@ -34,7 +35,7 @@ _SIGNATURES = {
     "tn_attn_prep": [_vp, _vp, _i, _i, _vp],
     "tn_attn_fwd_bf16": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
     "tn_attn_bwd_bf16": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64,
-                         _vp, _i64, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
+                         _vp, _i64, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "tn_fbank_f32": [_vp, _i, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp],
     "tn_logmel_power_f32": [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
     "tn_logmel_finish_f32": [_vp, _vp, _vp, _i, _i64, _i, _vp],

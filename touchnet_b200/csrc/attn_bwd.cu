@@ -50,6 +50,10 @@ struct AttnBwdParams {
   int B, T, H, KV, nblk;
   int Tq, q_blk_off;   // context parallelism: Q/dO/dQ/lse/delta hold rows [q_blk_off*128, +Tq) of the global sequence
   float scale, scale_log2;
+  // fused inverse RoPE (backward of hf apply_rotary_pos_emb, modeling_llama.py:151-168) on dQ and dK in the epilogue:
+  // cos/sin [rows, 64] bf16 indexed like the output tensor's rows (NULL = gradients w.r.t. the rotated q/k)
+  const bf16* rope_cos;
+  const bf16* rope_sin;
 };
 
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ O, int64_t ldo,
@@ -352,19 +356,55 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       const uint32_t acc_t = (grp == 0 ? tmem_acc1 : tmem_acc2) + lane_sel;
       uint8_t* stg = sT + grp * RES_BYTES;
       const float mul = (DKDV && grp == 0) ? 1.f : p.scale;  // dV unscaled; dK, dQ carry the softmax scale
+      const bool rope = p.rope_cos != nullptr && !(DKDV && grp == 0);   // dV is never rotated
+      if (!rope) {
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t o[32];
-        tmem_ld32(acc_t + c4 * 32, o);
-        tmem_ld_wait();
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t o[32];
+          tmem_ld32(acc_t + c4 * 32, o);
+          tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint32_t w[4];
+          for (int u = 0; u < 4; ++u) {
+            uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            w[e] = pack_bf16x2(__uint_as_float(o[u * 8 + 2 * e]) * mul, __uint_as_float(o[u * 8 + 2 * e + 1]) * mul);
-          const int colx = c4 * 32 + u * 8;
-          sts_u4(smem_u32(stg) + (colx >> 6) * RES_CHUNK + sw128_off(r, (colx & 63) >> 3), make_uint4(w[0], w[1], w[2], w[3]));
+            for (int e = 0; e < 4; ++e)
+              w[e] = pack_bf16x2(__uint_as_float(o[u * 8 + 2 * e]) * mul, __uint_as_float(o[u * 8 + 2 * e + 1]) * mul);
+            const int colx = c4 * 32 + u * 8;
+            sts_u4(smem_u32(stg) + (colx >> 6) * RES_CHUNK + sw128_off(r, (colx & 63) >> 3), make_uint4(w[0], w[1], w[2], w[3]));
+          }
+        }
+      } else {
+        // d/dx of y = x*cos + rotate_half(x)*sin :  dx_lo = g_lo*cos + g_hi*sin,  dx_hi = g_hi*cos - g_lo*sin
+        // (pairs (j, j+64) live in column chunks c4 and c4+2 of this thread's row)
+        const int64_t trow = int64_t(b) * res_rows + r0l + int(r);
+        const bool row_ok = r0l + int(r) < res_rows;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t lo[32], hi[32];
+          tmem_ld32(acc_t + half * 32, lo);
+          tmem_ld32(acc_t + 64 + half * 32, hi);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 c4v = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), s4v = make_uint4(0, 0, 0, 0);
+            if (row_ok) {
+              c4v = *reinterpret_cast<const uint4*>(p.rope_cos + trow * 64 + half * 32 + u * 8);
+              s4v = *reinterpret_cast<const uint4*>(p.rope_sin + trow * 64 + half * 32 + u * 8);
+            }
+            const uint32_t cw[4] = {c4v.x, c4v.y, c4v.z, c4v.w}, sw[4] = {s4v.x, s4v.y, s4v.z, s4v.w};
+            uint32_t wl[4], wh[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float gl0 = __uint_as_float(lo[u * 8 + 2 * e]) * mul, gl1 = __uint_as_float(lo[u * 8 + 2 * e + 1]) * mul;
+              const float gh0 = __uint_as_float(hi[u * 8 + 2 * e]) * mul, gh1 = __uint_as_float(hi[u * 8 + 2 * e + 1]) * mul;
+              const float c0 = bf16lo(cw[e]), c1 = bf16hi(cw[e]), s0 = bf16lo(sw[e]), s1 = bf16hi(sw[e]);
+              wl[e] = pack_bf16x2(fmaf(gl0, c0, gh0 * s0), fmaf(gl1, c1, gh1 * s1));
+              wh[e] = pack_bf16x2(fmaf(gh0, c0, -gl0 * s0), fmaf(gh1, c1, -gl1 * s1));
+            }
+            const uint32_t unit = uint32_t(half * 4 + u);     // 16-byte unit inside the 64-column chunk
+            sts_u4(smem_u32(stg) + sw128_off(r, unit), make_uint4(wl[0], wl[1], wl[2], wl[3]));
+            sts_u4(smem_u32(stg) + RES_CHUNK + sw128_off(r, unit), make_uint4(wh[0], wh[1], wh[2], wh[3]));
+          }
         }
       }
       fence_proxy_async_smem();
@@ -395,10 +435,13 @@ extern "C" int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64
                                 const void* O, int64_t ldo, const void* dO, int64_t lddo, const float* lse, float* delta,
                                 void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv,
                                 const int32_t* doc_ids, const int32_t* meta, int B, int T, int H, int KV, float scale,
-                                int Tq, int q_blk_off, tn_stream_t stream_) {
+                                int Tq, int q_blk_off, const void* rope_cos_q, const void* rope_sin_q,
+                                const void* rope_cos_k, const void* rope_sin_k, tn_stream_t stream_) {
   clear_error();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TN_REQUIRE(Q && K && V && O && dO && lse && delta && dQ && dK && dV && doc_ids && meta, "tn_attn_bwd_bf16: null pointer");
+  TN_REQUIRE((rope_cos_q == nullptr) == (rope_sin_q == nullptr) && (rope_cos_k == nullptr) == (rope_sin_k == nullptr),
+             "tn_attn_bwd_bf16: cos and sin tables come in pairs");
   TN_REQUIRE(B > 0 && T > 0 && H > 0 && KV > 0 && H % KV == 0, "tn_attn_bwd_bf16: bad dims");
   TN_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 &&
                  lddk % 8 == 0 && lddv % 8 == 0, "tn_attn_bwd_bf16: strides must be multiples of 8");
@@ -444,12 +487,14 @@ extern "C" int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64
   {
     AttnBwdParams pk = p;
     pk.out1 = static_cast<bf16*>(dV); pk.ld1 = lddv; pk.out2 = static_cast<bf16*>(dK); pk.ld2 = lddk;
+    pk.rope_cos = static_cast<const bf16*>(rope_cos_k); pk.rope_sin = static_cast<const bf16*>(rope_sin_k);
     attn_bwd_kernel<true><<<dim3(nblk, KV, B), BWD_THREADS, BwdSmem::ALLOC, stream>>>(k128, v128, q64, do64, mdv, mdk, pk);
     TN_CHECK_CUDA(cudaGetLastError());
   }
   {
     AttnBwdParams pq = p;
     pq.out1 = static_cast<bf16*>(dQ); pq.ld1 = lddq; pq.out2 = nullptr; pq.ld2 = 0;
+    pq.rope_cos = static_cast<const bf16*>(rope_cos_q); pq.rope_sin = static_cast<const bf16*>(rope_sin_q);
     attn_bwd_kernel<false><<<dim3(nqb, H, B), BWD_THREADS, BwdSmem::ALLOC, stream>>>(q128, do128, k64, v64, mdq, mdq, pq);
     TN_CHECK_CUDA(cudaGetLastError());
   }

@@ -341,7 +341,8 @@ int gemm_pair_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int6
 int gemm_pair_swiglu_dispatch(const void* X, int64_t ldx, const void* Wg, const void* Wu, int64_t ldw, void* G, void* U,
                               void* H, int64_t ldh, int M, int N, int K, cudaStream_t stream);
 int gemm_pair_seg_dispatch(int mode, const void* A, int64_t lda, const void* const* Bs, int64_t ldb, void* const* Ds,
-                           int64_t ldd, int d_f32, const int* seg, int M, int N, int K, cudaStream_t stream);
+                           int64_t ldd, int d_f32, const int* seg, int M, int N, int K, const void* rope_cos,
+                           const void* rope_sin, cudaStream_t stream);
 // TN_GEMM_PAIR=0 forces the single-CTA kernels (A/B measurements); default: CTA pairs whenever the tile fits
 static bool use_pair() {
   static int v = -1;
@@ -431,7 +432,7 @@ extern "C" int tn_gemm_swiglu_bf16(const void* X, int64_t ldx, const void* Wg, c
 
 extern "C" int tn_gemm_qkv_bf16(int mode, const void* A, int64_t lda, const void* B0, const void* B1, const void* B2,
                                 int64_t ldb, void* D0, void* D1, void* D2, int64_t ldd, int d_f32, int s0, int s1, int s2,
-                                int M, int N, int K, tn_stream_t stream_) {
+                                int M, int N, int K, const void* rope_cos, const void* rope_sin, tn_stream_t stream_) {
   clear_error();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TN_REQUIRE(A && B0 && D0, "tn_gemm_qkv_bf16: null pointer");
@@ -448,5 +449,7 @@ extern "C" int tn_gemm_qkv_bf16(int mode, const void* A, int64_t lda, const void
   const void* Bs[3] = {B0, B1, B2};
   void* Ds[3] = {D0, D1, D2};
   const int seg[3] = {s0, s1, s2};
-  return gemm_pair_seg_dispatch(mode, A, lda, Bs, ldb, Ds, ldd, d_f32, seg, M, N, K, stream);
+  TN_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "tn_gemm_qkv_bf16: cos and sin tables come in pairs");
+  TN_REQUIRE(rope_cos == nullptr || mode == 0, "tn_gemm_qkv_bf16: fused RoPE exists for the forward projection only");
+  return gemm_pair_seg_dispatch(mode, A, lda, Bs, ldb, Ds, ldd, d_f32, seg, M, N, K, rope_cos, rope_sin, stream);
 }

@@ -42,6 +42,12 @@ struct PairParams {
   //   d_seg 1: D = [D0;D1;D2] stacked along M (fused QKV wgrad: one dW per parameter)
   int b_seg, d_seg;
   int off1, off2;
+  // fused RoPE in the epilogue of the QKV forward (hf apply_rotary_pos_emb, modeling_llama.py:151-168): output columns
+  // below rope_end (the q and k segments, heads of 128 columns) are rotated with the per-row cos/sin tables
+  // [M, 64] bf16 (tn_rope_table); same bf16 rounding points as the unfused kernel -> bit-identical results
+  const bf16* rope_cos;
+  const bf16* rope_sin;
+  int rope_end;
 };
 
 __device__ __forceinline__ void pair_decode_tile(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
@@ -244,6 +250,59 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         constexpr int CW = (EPI == 2) ? 32 : 64;   // columns per staging round (128 B per row)
         const int n0 = n_blk * P_BN;
+        if (EPI == 0 && p.rope_cos != nullptr && n0 < p.rope_end) {
+          // ---- RoPE tile: 2 heads of 128 columns; pairs (j, j+64) sit in this thread's row ----
+          const bool row_ok = row < p.M;
+#pragma unroll 1
+          for (int head = 0; head < 2; ++head) {
+            if (n_issued > 0) {
+              if (etid == 0) tma_store_wait_read<0>();
+              named_bar(2, 128);
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t lo[32], hi[32];
+              tmem_ld32(t_row + head * 128 + half * 32, lo);
+              tmem_ld32(t_row + head * 128 + 64 + half * 32, hi);
+              tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint4 c4v = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), s4v = make_uint4(0, 0, 0, 0);
+                if (row_ok) {
+                  c4v = *reinterpret_cast<const uint4*>(p.rope_cos + int64_t(row) * 64 + half * 32 + u * 8);
+                  s4v = *reinterpret_cast<const uint4*>(p.rope_sin + int64_t(row) * 64 + half * 32 + u * 8);
+                }
+                const uint32_t cw[4] = {c4v.x, c4v.y, c4v.z, c4v.w}, sw[4] = {s4v.x, s4v.y, s4v.z, s4v.w};
+                uint32_t wl[4], wh[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float a[2] = {bf16_round(__uint_as_float(lo[u * 8 + 2 * e])), bf16_round(__uint_as_float(lo[u * 8 + 2 * e + 1]))};
+                  float bb[2] = {bf16_round(__uint_as_float(hi[u * 8 + 2 * e])), bf16_round(__uint_as_float(hi[u * 8 + 2 * e + 1]))};
+                  const float c[2] = {bf16lo(cw[e]), bf16hi(cw[e])}, sn[2] = {bf16lo(sw[e]), bf16hi(sw[e])};
+                  float o1[2], o2[2];
+#pragma unroll
+                  for (int t2 = 0; t2 < 2; ++t2) {
+                    o1[t2] = bf16_round(a[t2] * c[t2]) + bf16_round(-bb[t2] * sn[t2]);
+                    o2[t2] = bf16_round(bb[t2] * c[t2]) + bf16_round(a[t2] * sn[t2]);
+                  }
+                  wl[e] = pack_bf16x2(o1[0], o1[1]);
+                  wh[e] = pack_bf16x2(o2[0], o2[1]);
+                }
+                const uint32_t off = r * 128u + ((uint32_t(half * 4 + u) ^ (r & 7u)) << 4);
+                *reinterpret_cast<uint4*>(sStg + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                *reinterpret_cast<uint4*>(sStg + P_STG_BYTES + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+              }
+            }
+            fence_proxy_async_smem();
+            named_bar(2, 128);
+            if (etid == 0) {
+              tma_store_2d(&tmD, sStg, n0 + head * 128, row0);
+              tma_store_2d(&tmD, sStg + P_STG_BYTES, n0 + head * 128 + 64, row0);
+              tma_store_commit();
+            }
+            n_issued += 2;
+          }
+        } else {
         const CUtensorMap* dmap = &tmD;
         int drow0 = row0;
         if (p.d_seg == 1) {                       // output rows belong to one of several gradient tensors
@@ -255,7 +314,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = 0; c < P_BN; c += CW) {
           uint8_t* stg = sStg + (n_issued & 1u) * P_STG_BYTES;
           if (n_issued >= 2) {
-            if (etid == 0) tma_store_wait_read<1>();   // the store that last read this buffer has drained it
+            if (etid == 0) {
+              // the store that last read this buffer has drained it (RoPE tiles commit both buffers in one group)
+              if (EPI == 0 && p.rope_cos != nullptr) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            }
             named_bar(2, 128);
           }
           const int col = n0 + c;
@@ -326,6 +388,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           ++n_issued;
         }
+        }   // (non-RoPE tile)
       }
       tc_fence_before();
       __syncwarp();
@@ -394,8 +457,13 @@ int gemm_pair_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int6
 // (B K-major), 1 = dgrad  D[M,N] = [A0|A1|A2]·[B0;B1;B2] (A = one [M, k0+k1+k2] buffer, B MN-major, segmented along K),
 // 2 = wgrad  [D0;D1;D2] = Aᵀ·X (A = one [Mred, m0+m1+m2] buffer MN-major, B MN-major, D segmented along M).
 int gemm_pair_seg_dispatch(int mode, const void* A, int64_t lda, const void* const* Bs, int64_t ldb, void* const* Ds,
-                           int64_t ldd, int d_f32, const int* seg, int M, int N, int K, cudaStream_t stream) {
+                           int64_t ldd, int d_f32, const int* seg, int M, int N, int K, const void* rope_cos,
+                           const void* rope_sin, cudaStream_t stream) {
   PairParams p{};
+  if (mode == 0 && rope_cos && rope_sin) {
+    p.rope_cos = static_cast<const bf16*>(rope_cos); p.rope_sin = static_cast<const bf16*>(rope_sin);
+    p.rope_end = seg[0] + seg[1];
+  }
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
   p.off1 = seg[0]; p.off2 = seg[0] + seg[1];

@@ -166,13 +166,15 @@ def qkv_fusable(M: int, nq: int, nkv: int) -> bool:
     return _FUSE_QKV and M >= 256 and nq % 256 == 0 and nkv % 256 == 0
 
 
-def gemm_qkv_fwd(x, wq, wk, wv):
-    """qkv[M, nq+2nkv] = x·[Wq;Wk;Wv]ᵀ in one launch (weights stay separate tensors)."""
+def gemm_qkv_fwd(x, wq, wk, wv, rope=None):
+    """qkv[M, nq+2nkv] = x·[Wq;Wk;Wv]ᵀ in one launch (weights stay separate tensors).  rope = (cos, sin) tables
+    [M, 64]: RoPE is applied to the q and k columns in the GEMM epilogue."""
     M, K = x.shape
     nq, nkv = wq.shape[0], wk.shape[0]
     out = torch.empty((M, nq + 2 * nkv), dtype=BF16, device=x.device)
     _lib.call("tn_gemm_qkv_bf16", 0, x.data_ptr(), x.stride(0), wq.data_ptr(), wk.data_ptr(), wv.data_ptr(), wq.stride(0),
-              out.data_ptr(), None, None, out.stride(0), 0, nq, nkv, nkv, M, nq + 2 * nkv, K, _st())
+              out.data_ptr(), None, None, out.stride(0), 0, nq, nkv, nkv, M, nq + 2 * nkv, K,
+              None if rope is None else rope[0].data_ptr(), None if rope is None else rope[1].data_ptr(), _st())
     return out
 
 
@@ -183,7 +185,7 @@ def gemm_qkv_dgrad(dqkv, wq, wk, wv):
     out = torch.empty((M, d), dtype=BF16, device=dqkv.device)
     _lib.call("tn_gemm_qkv_bf16", 1, dqkv.data_ptr(), dqkv.stride(0), wq.data_ptr(), wk.data_ptr(), wv.data_ptr(),
               wq.stride(0), out.data_ptr(), None, None, out.stride(0), 0, wq.shape[0], wk.shape[0], wv.shape[0], M, d, Kt,
-              _st())
+              None, None, _st())
     return out
 
 
@@ -198,7 +200,8 @@ def gemm_qkv_wgrad(dqkv, x, f32: bool, nq: int | None = None, nkv: int | None = 
     dt = torch.float32 if f32 else BF16
     outs = [torch.empty((n, d), dtype=dt, device=x.device) for n in (nq, nkv, nkv)]
     _lib.call("tn_gemm_qkv_bf16", 2, dqkv.data_ptr(), dqkv.stride(0), x.data_ptr(), None, None, x.stride(0),
-              outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), d, int(f32), nq, nkv, nkv, Mt, d, Mred, _st())
+              outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), d, int(f32), nq, nkv, nkv, Mt, d, Mred, None,
+              None, _st())
     return outs
 
 
@@ -298,8 +301,10 @@ def attn_fwd(q, k, v, plan: AttnPlan, H: int, KV: int, scale: float):
     return o, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, plan: AttnPlan, H: int, KV: int, scale: float, out=None):
-    """`out` = (dq, dk, dv) preallocated (possibly strided views of one [B*T, (H+2KV)*128] buffer)."""
+def attn_bwd(q, k, v, o, do, lse, plan: AttnPlan, H: int, KV: int, scale: float, out=None, rope=None):
+    """`out` = (dq, dk, dv) preallocated (possibly strided views of one [B*T, (H+2KV)*128] buffer).
+    `rope` = (cos, sin) tables: the kernels' epilogues apply the inverse rotation, i.e. dq/dk come back w.r.t. the
+    un-rotated projections (only without context parallelism, where dK rows and table rows coincide)."""
     B, T = plan.B, plan.T
     Tq = plan.Tq
     if out is None:
@@ -314,7 +319,9 @@ def attn_bwd(q, k, v, o, do, lse, plan: AttnPlan, H: int, KV: int, scale: float,
     _lib.call("tn_attn_bwd_bf16", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
               o.data_ptr(), o.stride(0), do.data_ptr(), do.stride(0), lse.data_ptr(), delta.data_ptr(),
               dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0),
-              plan.doc.data_ptr(), plan.meta.data_ptr(), B, T, H, KV, float(scale), Tq, plan.q_blk_off, _st())
+              plan.doc.data_ptr(), plan.meta.data_ptr(), B, T, H, KV, float(scale), Tq, plan.q_blk_off,
+              None if rope is None else rope[0].data_ptr(), None if rope is None else rope[1].data_ptr(),
+              None if rope is None else rope[0].data_ptr(), None if rope is None else rope[1].data_ptr(), _st())
     return dq, dk, dv
 
 
@@ -420,9 +427,7 @@ class PackedAttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, do):
         q, k, v, o, lse, cos, sin = ctx.saved_tensors
-        dq, dk, dv = attn_bwd(q, k, v, o, do, lse, ctx.plan, ctx.H, ctx.KV, ctx.scale)
-        rope_apply_(dq, cos, sin, ctx.H, 128, inverse=True)
-        rope_apply_(dk, cos, sin, ctx.KV, 128, inverse=True)
+        dq, dk, dv = attn_bwd(q, k, v, o, do, lse, ctx.plan, ctx.H, ctx.KV, ctx.scale, rope=(cos, sin))
         return dq, dk, dv, None, None, None, None, None, None
 
 
@@ -482,15 +487,17 @@ class DecoderLayerFn(torch.autograd.Function):
         scale = 1.0 / math.sqrt(128)
         h1, _, rstd1 = rmsnorm_fwd(x2, ln1, eps)
         nq, nkv = wq.shape[0], wk.shape[0]
+        rope_in_gemm = qkv_fusable(x2.shape[0], nq, nkv) and bq is None     # RoPE in the QKV GEMM epilogue
         if qkv_fusable(x2.shape[0], nq, nkv):
-            qkv = gemm_qkv_fwd(h1, wqb, wkb, wvb)
+            qkv = gemm_qkv_fwd(h1, wqb, wkb, wvb, rope=(cos, sin) if rope_in_gemm else None)
             q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
         else:
             q = gemm(h1, wqb); k = gemm(h1, wkb); v = gemm(h1, wvb)
         if bq is not None:
             q += bq.to(BF16); k += bk.to(BF16); v += bv.to(BF16)
-        rope_apply_(q, cos, sin, H, 128)
-        rope_apply_(k, cos, sin, KV, 128)
+        if not rope_in_gemm:
+            rope_apply_(q, cos, sin, H, 128)
+            rope_apply_(k, cos, sin, KV, 128)
         if plan.cp_group is None:
             o, lse = attn_fwd(q, k, v, plan, H, KV, scale)
         else:   # context parallel: K/V of all cp ranks are gathered, the kernel runs on this rank's query window
@@ -537,14 +544,14 @@ class DecoderLayerFn(torch.autograd.Function):
             if fused:
                 dqkv = torch.cat([dq, dk, dv], dim=1)
                 dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
-        elif fused:
+            rope_apply_(dq, cos, sin, H, 128, inverse=True)
+            rope_apply_(dk, cos, sin, KV, 128, inverse=True)
+        elif fused:   # inverse RoPE happens in the attention-backward epilogues
             dqkv = torch.empty((x2.shape[0], nq + 2 * nkv), dtype=BF16, device=x2.device)
             dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
-            attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale, out=(dq, dk, dv))
+            attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale, out=(dq, dk, dv), rope=(cos, sin))
         else:
-            dq, dk, dv = attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale)
-        rope_apply_(dq, cos, sin, H, 128, inverse=True)
-        rope_apply_(dk, cos, sin, KV, 128, inverse=True)
+            dq, dk, dv = attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale, rope=(cos, sin))
         if fused:
             dh1 = gemm_qkv_dgrad(dqkv, wqb, wkb, wvb)
             dwq, dwk, dwv = gemm_qkv_wgrad(dqkv, h1, f32, nq, nkv)

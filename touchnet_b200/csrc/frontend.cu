@@ -56,6 +56,25 @@ __device__ __forceinline__ int find_utt(const int64_t* __restrict__ frame_offset
   return lo;
 }
 
+// non-zero span [lo, hi) of every (triangular) mel filter row: one warp per row, lanes stride over the bins
+__device__ __forceinline__ void mel_spans(const float* __restrict__ filters, int n_mels, int n_bins, int* mel_lo,
+                                          int* mel_hi) {
+  const int nwarps = blockDim.x >> 5;
+  const uint32_t lane = lane_id();
+  for (int m = warp_id(); m < n_mels; m += nwarps) {
+    const float* w = filters + int64_t(m) * n_bins;
+    int lo = n_bins, hi = 0;
+    for (int k = lane; k < n_bins; k += 32)
+      if (__ldg(w + k) != 0.f) { lo = min(lo, k); hi = max(hi, k + 1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { mel_lo[m] = lo; mel_hi[m] = hi; }
+  }
+}
+
 // MODE 0: kaldi fbank (snip_edges, DC removal, pre-emphasis, window, zero-pad to n_fft, log(max(x, eps)))
 // MODE 1: whisper log-mel (center + reflect padding, window length == n_fft, log10(max(x, 1e-10)), per-utt max)
 template <int MODE>
@@ -77,14 +96,7 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FrontendPara
     sincospif(2.0f * float(i) / float(n_fft), &s, &c);
     tab[i] = make_float2(c, s);
   }
-  // non-zero span of every (triangular) mel filter row
-  for (int m = tid; m < p.n_mels; m += FE_THREADS) {
-    const float* w = p.mel_filters + int64_t(m) * n_bins;
-    int lo = n_bins, hi = 0;
-    for (int k = 0; k < n_bins; ++k)
-      if (w[k] != 0.f) { lo = min(lo, k); hi = k + 1; }
-    mel_lo[m] = lo; mel_hi[m] = hi;
-  }
+  mel_spans(p.mel_filters, p.n_mels, n_bins, mel_lo, mel_hi);
   __syncthreads();
 
   const int64_t n_groups = (p.total_frames + FE_FRAMES - 1) / FE_FRAMES;
@@ -264,6 +276,7 @@ __global__ void __launch_bounds__(256) feat_stack_kernel(const float* __restrict
 // ~10 kFLOP per frame instead of ~410 kFLOP for the table DFT; HBM traffic unchanged (the algorithmic minimum).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int FF_N = 512, FF_H = 256, FF_WARPS = 8, FF_LOG2H = 8;
+constexpr int FF_MAX_UTT_TAB = 512;   // utterances per launch whose offsets are staged in shared memory
 
 __device__ __forceinline__ uint32_t bitrev8(uint32_t x) { return __brev(x) >> 24; }
 
@@ -273,7 +286,9 @@ __global__ void __launch_bounds__(FF_WARPS * 32) fbank_fft_kernel(const Frontend
   float2* w512 = w256 + FF_H / 2;                                // [257]  exp(-2*pi*i*k/512)
   int* mel_lo = reinterpret_cast<int*>(w512 + FF_H + 1 + 1);     // [n_mels]
   int* mel_hi = mel_lo + FE_MAX_MELS;
-  float2* zbase = reinterpret_cast<float2*>(mel_hi + FE_MAX_MELS);  // per warp: z[256] then ps[260]
+  int64_t* s_frm_off = reinterpret_cast<int64_t*>(mel_hi + FE_MAX_MELS);   // [FF_MAX_UTT_TAB]
+  int64_t* s_utt_off = s_frm_off + FF_MAX_UTT_TAB;                        // [FF_MAX_UTT_TAB]
+  float2* zbase = reinterpret_cast<float2*>(s_utt_off + FF_MAX_UTT_TAB);   // per warp: z[256] then ps[260]
   constexpr int PER_WARP = FF_H * 2 + 260;                       // floats
   const uint32_t warp = warp_id(), lane = lane_id();
   float2* z = reinterpret_cast<float2*>(reinterpret_cast<float*>(zbase) + warp * PER_WARP);
@@ -290,21 +305,21 @@ __global__ void __launch_bounds__(FF_WARPS * 32) fbank_fft_kernel(const Frontend
     w512[i] = make_float2(cs, sn);
   }
   const int n_bins = FF_H + 1;
-  for (int m = tid; m < p.n_mels; m += blockDim.x) {
-    const float* w = p.mel_filters + int64_t(m) * n_bins;
-    int lo = n_bins, hi = 0;
-    for (int k = 0; k < n_bins; ++k)
-      if (w[k] != 0.f) { lo = min(lo, k); hi = k + 1; }
-    mel_lo[m] = lo; mel_hi[m] = hi;
-  }
+  mel_spans(p.mel_filters, p.n_mels, n_bins, mel_lo, mel_hi);
+  // utterance offset tables in shared memory: the per-frame binary search then never leaves the SM
+  const int n_tab = min(p.n_utts + 1, FF_MAX_UTT_TAB);
+  for (int i = tid; i < n_tab; i += blockDim.x) { s_frm_off[i] = p.frame_offsets[i]; s_utt_off[i] = p.utt_offsets[i]; }
   __syncthreads();
+  const bool tab_ok = p.n_utts + 1 <= FF_MAX_UTT_TAB;
+  const int64_t* frm_off = tab_ok ? s_frm_off : p.frame_offsets;
+  const int64_t* utt_off = tab_ok ? s_utt_off : p.utt_offsets;
 
   const int64_t warps_total = int64_t(gridDim.x) * FF_WARPS;
   for (int64_t frame = int64_t(blockIdx.x) * FF_WARPS + warp; frame < p.total_frames; frame += warps_total) {
     // ---- framing: DC removal, pre-emphasis, window; packed bit-reversed into z ----
-    const int u = find_utt(p.frame_offsets, p.n_utts, frame);
-    const int64_t fi = frame - p.frame_offsets[u];
-    const int64_t wav0 = p.utt_offsets[u] + fi * p.frame_shift;
+    const int u = find_utt(frm_off, p.n_utts, frame);
+    const int64_t fi = frame - frm_off[u];
+    const int64_t wav0 = utt_off[u] + fi * p.frame_shift;
     constexpr int PER_LANE = FF_N / 32;  // 16
     float v[PER_LANE];
     float sum = 0.f;
@@ -377,7 +392,7 @@ __global__ void __launch_bounds__(FF_WARPS * 32) fbank_fft_kernel(const Frontend
 
 static int launch_fbank_fft(const FrontendParams& p, cudaStream_t stream) {
   const size_t smem = sizeof(float2) * (FF_H / 2 + FF_H + 2) + sizeof(int) * 2 * FE_MAX_MELS +
-                      sizeof(float) * FF_WARPS * (FF_H * 2 + 260);
+                      sizeof(int64_t) * 2 * FF_MAX_UTT_TAB + sizeof(float) * FF_WARPS * (FF_H * 2 + 260);
   const int64_t n_groups = (p.total_frames + FF_WARPS - 1) / FF_WARPS;
   int64_t grid = int64_t(sm_count()) * 6;
   if (grid > n_groups) grid = n_groups;

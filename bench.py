@@ -373,9 +373,17 @@ def main():
         mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("dp_shard",))
         mp = MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.float32)
         layers = model.language_model.model.layers       # ref: touchnet/models/helper_func.py:134-202 apply_fsdp
+        # TN_FSDP_RESHARD=0 keeps the bf16 parameters gathered between forward and backward (16 GB more per GPU, one
+        # all-gather per layer per step instead of two); default follows the reference (reshard, last block excepted)
+        reshard = os.environ.get("TN_FSDP_RESHARD", "1") != "0"
         for i, layer in enumerate(layers):
-            fully_shard(layer, mesh=mesh, mp_policy=mp, reshard_after_forward=(i < len(layers) - 1))
-        fully_shard(model, mesh=mesh, mp_policy=mp, reshard_after_forward=True)
+            fully_shard(layer, mesh=mesh, mp_policy=mp, reshard_after_forward=(reshard and i < len(layers) - 1))
+        fully_shard(model, mesh=mesh, mp_policy=mp, reshard_after_forward=reshard)
+        depth = int(os.environ.get("TN_FSDP_PREFETCH", "0"))
+        if depth > 0:                                    # explicit prefetch of the next `depth` blocks' all-gathers
+            for i, layer in enumerate(layers):
+                layer.set_modules_to_forward_prefetch(list(layers[i + 1:i + 1 + depth]))
+                layer.set_modules_to_backward_prefetch(list(reversed(layers[max(0, i - depth):i])))
     model.train()
 
     host, meta = make_host_batch(dist_util_seed(2025, rank), B, T, cfg.text_config.vocab_size)

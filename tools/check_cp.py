@@ -35,14 +35,17 @@ Tl = T // world
 sl = slice(rank * Tl, (rank + 1) * Tl)
 context_parallel.enable_context_parallel(model, dist.group.WORLD)
 lg = model(input_ids=ids[:, sl].contiguous(), attention_mask=doc[:, sl].contiguous(), position_ids=pos[:, sl].contiguous()).logits
-loss = ((lg.float() * tgt[:, sl])[doc[:, sl] > 0]).sum() / n_valid          # same global mean
+loss = ((lg.float() * tgt[:, sl])[doc[:, sl] > 0]).sum() / (n_valid * cfg.vocab_size)   # same global mean
 loss.backward()
 err_fwd = float((lg.float() - ref_logits[:, sl].float()).abs().max())
 worst = 0.0
 for n, p in model.named_parameters():
     gsum = p.grad.detach().clone()
     dist.all_reduce(gsum)                                                    # ranks hold partial sums over their tokens
-    worst = max(worst, rel_err(gsum.float(), ref_grads[n].float()))
+    e = rel_err(gsum.float(), ref_grads[n].float())
+    if rank == 0 and (e > 2e-2 or os.environ.get("CP_VERBOSE")):
+        print(f"  {n}: rel err {e:.4g} |ref| {float(ref_grads[n].float().norm()):.4g} |cp| {float(gsum.float().norm()):.4g}")
+    worst = max(worst, e)
 res = torch.tensor([err_fwd, worst], device=dev)
 dist.all_reduce(res, op=dist.ReduceOp.MAX)
 if rank == 0:

@@ -282,7 +282,7 @@ class B200LlamaForCausalLM(nn.Module):
                 position_ids: Optional[torch.Tensor] = None, past_key_values=None,
                 inputs_embeds: Optional[torch.Tensor] = None, labels=None, use_cache=None, **kwargs: Any):
         assert labels is None, "loss is computed in the train loop (ref: modeling_touch_audio.py:121)"
-        ops.prefetch_bf16_weights(self)     # side-stream casts of stale fp32 master weights (no-op under FSDP2 / when fresh)
+        ops.begin_forward(self)             # side-stream casts of stale fp32 master weights / new cache epoch under FSDP2
         if inputs_embeds is None:
             if input_ids is None:
                 raise TouchNetB200Error("either input_ids or inputs_embeds is required")
@@ -355,7 +355,7 @@ class B200TouchAudioForCausalLM(nn.Module):
                 output_attentions=None, output_hidden_states=None, return_dict=None, cache_position=None,
                 logits_to_keep=0, check_nan: bool = False, **kwargs: Any):
         assert labels is None  # we calculate loss in train-loop (ref: modeling_touch_audio.py:121)
-        ops.prefetch_bf16_weights(self)     # projector, decoder layers, lm_head: casts overlap the GEMMs in front of them
+        ops.begin_forward(self)             # projector, decoder layers, lm_head: casts overlap the GEMMs in front of them
         if inputs_embeds is None:
             lm = self.language_model
             proj = None

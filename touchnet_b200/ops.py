@@ -53,7 +53,7 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
 def bf16_weight(w: torch.Tensor) -> torch.Tensor:
     """bf16 working copy of a parameter: the tensor itself if already bf16 (FSDP2 mixed precision hands the modules
     bf16 unsharded parameters), else a cast of the fp32 master cached ON THE PARAMETER OBJECT (attribute `_tn_bf16` =
-    (version, tensor, event), keyed by the parameter's version counter) so that it lives and dies with the parameter and
+    (version, tensor, event, epoch), keyed by the parameter's version counter) so that it lives and dies with the parameter and
     one step casts once.  Call it with the nn.Parameter itself (module level), not from inside an autograd Function.
     If the copy was produced ahead of time on the side stream (`prefetch_bf16_weights`), the current stream is made to
     wait for it here."""
@@ -62,14 +62,34 @@ def bf16_weight(w: torch.Tensor) -> torch.Tensor:
         return w if w.is_contiguous() else w.contiguous()
     ent = getattr(w, "_tn_bf16", None)
     ok = ent is not None and ent[1].shape == w.shape and ent[1].device == w.device
-    if ok and ent[0] == w._version:
+    if ok and ent[0] == w._version and ent[3] == _CACHE_EPOCH:
         if ent[2] is not None:
             torch.cuda.current_stream().wait_event(ent[2])
-            w._tn_bf16 = (ent[0], ent[1], None)
+            w._tn_bf16 = (ent[0], ent[1], None, ent[3])
         return ent[1]
     out = cast_bf16(w.detach(), ent[1] if ok else None)
-    w._tn_bf16 = (w._version, out, None)
+    w._tn_bf16 = (w._version, out, None, _CACHE_EPOCH)
     return out
+
+
+# FSDP2 refills its unsharded fp32 parameters (param_dtype=None) under `_unsafe_preserve_version_counter`, so the version
+# key alone would serve stale copies there: models that find themselves FSDP-managed bump this epoch every forward.
+_CACHE_EPOCH = 0
+
+
+def begin_forward(module: torch.nn.Module) -> None:
+    """Called at the top of the model forwards: starts a new cache epoch when parameters are FSDP-managed (casts happen
+    once per forward, like the all-gather), else issues the side-stream prefetch of stale fp32 master weights."""
+    global _CACHE_EPOCH
+    try:
+        from torch.distributed.fsdp import FSDPModule
+        managed = any(isinstance(m, FSDPModule) for m in module.modules())
+    except ImportError:
+        managed = False
+    if managed:
+        _CACHE_EPOCH += 1
+    else:
+        prefetch_bf16_weights(module)
 
 
 def invalidate_bf16_cache(module: torch.nn.Module) -> None:
@@ -78,10 +98,18 @@ def invalidate_bf16_cache(module: torch.nn.Module) -> None:
     for p in module.parameters():
         ent = getattr(p, "_tn_bf16", None)
         if ent is not None:
-            p._tn_bf16 = (-1, ent[1], None)
+            p._tn_bf16 = (-1, ent[1], None, _CACHE_EPOCH)
 
 
 _CAST_STREAM: dict = {}
+
+
+def _is_dtensor(t) -> bool:
+    try:
+        from torch.distributed.tensor import DTensor
+    except Exception:       # torch built without distributed
+        return False
+    return isinstance(t, DTensor)
 
 
 def prefetch_bf16_weights(module: torch.nn.Module) -> int:
@@ -92,14 +120,17 @@ def prefetch_bf16_weights(module: torch.nn.Module) -> int:
     params, seen = [], set()
     for m in module.modules():          # nn.Linear weights are the only tensors consumed through bf16_weight()
         w = getattr(m, "weight", None) if isinstance(m, torch.nn.Linear) else None
-        if w is not None and w.dtype == torch.float32 and w.is_cuda and id(w) not in seen:
-            seen.add(id(w))
-            params.append(w)
+        if w is None or w.dtype != torch.float32 or not w.is_cuda or id(w) in seen:
+            continue
+        if _is_dtensor(w) or w.untyped_storage().size() == 0:
+            continue                    # FSDP2/TP-managed: the all-gather delivers bf16 (MixedPrecisionPolicy), nothing to cast
+        seen.add(id(w))
+        params.append(w)
     todo = []
     for p in params:
         ent = getattr(p, "_tn_bf16", None)
         ok = ent is not None and ent[1].shape == p.shape and ent[1].device == p.device
-        if not (ok and ent[0] == p._version):
+        if not (ok and ent[0] == p._version and ent[3] == _CACHE_EPOCH):
             todo.append((p, ent[1] if ok else None))
     if not todo:
         return 0
@@ -115,7 +146,7 @@ def prefetch_bf16_weights(module: torch.nn.Module) -> int:
             out.record_stream(cur)
             ev = torch.cuda.Event()
             ev.record(side)
-            p._tn_bf16 = (p._version, out, ev)
+            p._tn_bf16 = (p._version, out, ev, _CACHE_EPOCH)
     return len(todo)
 
 

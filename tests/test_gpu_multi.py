@@ -34,3 +34,12 @@ def test_fsdp2_matches_single_gpu(fp32_params):
     concatenated batch, and the same loss after one SGD step (bf16 and fp32 all-gather dtypes)."""
     r = _torchrun("tools/check_fsdp.py", 2, 29542 + int(fp32_params), {"FSDP_FP32": fp32_params})
     assert r.returncode == 0 and "FSDP OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("audio", ["0", "1"])
+def test_tensor_parallel_matches_unsharded(audio):
+    """tp=2 with sequence parallelism (the reference's plan, parallelize_llama.py:105-196): logits and every parameter
+    gradient equal the unsharded run; audio=1 adds the projector, q/k/v bias and the vocabulary-parallel embedding add."""
+    r = _torchrun("tools/check_tp.py", 2, 29545 + int(audio), {"TP_AUDIO": audio})
+    assert r.returncode == 0 and "TP OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -1,0 +1,182 @@
+"""CPU, world_size 2 over gloo: the host logic of tensor parallelism (touchnet_b200/tensor_parallel.py) and context
+parallelism (touchnet_b200/context_parallel.py) - DTensor parameter sharding, the collectives inside the decoder block's
+forward/backward, vocabulary-parallel embedding / lm_head, gradient reductions - against the unsharded run of the same
+model.  The CUDA ops are replaced by plain-torch stand-ins (tests/cpu_ops_shim.py, test infrastructure only), so what is
+compared is exactly the wiring; kernel numerics are covered by the `-m gpu` tests and tests/test_gpu_multi.py."""
+import copy
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+class _Cfg:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _text_cfg(bias=False):
+    return _Cfg(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                head_dim=128, vocab_size=384, rms_norm_eps=1e-5, rope_theta=500000.0, rope_scaling=None,
+                attention_bias=bias, tie_word_embeddings=False, initializer_range=0.02, model_type="llama", pad_token_id=0)
+
+
+def _docs(B, T, lens):
+    doc = torch.zeros(B, T, dtype=torch.int64)
+    pos = torch.zeros(B, T, dtype=torch.int64)
+    for b, ls in enumerate(lens):
+        o = 0
+        for i, n in enumerate(ls):
+            doc[b, o:o + n] = i + 1
+            pos[b, o:o + n] = torch.arange(n)
+            o += n
+    return doc, pos
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _build(audio: bool, bias: bool):
+    from touchnet_b200 import modeling
+    torch.manual_seed(11)
+    text = _text_cfg(bias)
+    if audio:
+        model = modeling.B200TouchAudioForCausalLM(_Cfg(audio_config=_Cfg(input_size=80), text_config=text, pad_token_id=0))
+    else:
+        model = modeling.B200LlamaForCausalLM(text)
+    model.post_init()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 2:
+                p.normal_(0, 0.05)
+            elif "bias" in n:
+                p.normal_(0, 0.1)
+            else:
+                p.uniform_(0.5, 1.5)                      # norm weights away from 1 so their gradients matter
+    return model, text
+
+
+def _inputs(B, T, V, audio):
+    g = torch.Generator().manual_seed(5)
+    doc, pos = _docs(B, T, [[100, 120, 20], [256]][:B])
+    ids = torch.randint(1, V, (B, T), generator=g)
+    tgt = torch.randn(B, T, V, generator=g)
+    kw = dict(input_ids=ids, attention_mask=doc, position_ids=pos)
+    if audio:
+        is_audio = torch.zeros(B, T, dtype=torch.bool)
+        is_audio[:, :64] = True
+        kw["input_features"] = torch.randn(B, T, 80, generator=g) * is_audio[..., None]
+        kw["input_ids"] = torch.where(is_audio, torch.zeros_like(ids), ids)
+    return kw, doc, tgt
+
+
+def _loss(logits, tgt, doc, denom):
+    return ((logits.float() * tgt)[doc > 0]).sum() / denom
+
+
+def _tp_worker(rank, world, port, audio, bias, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import cpu_ops_shim
+        cpu_ops_shim.install()
+        from torch.distributed.device_mesh import init_device_mesh
+        from touchnet_b200 import tensor_parallel
+        model, text = _build(audio, bias)
+        B, T = 2, 256
+        kw, doc, tgt = _inputs(B, T, text.vocab_size, audio)
+        denom = float((doc > 0).sum()) * text.vocab_size
+        ref_model = copy.deepcopy(model)
+        ref_logits = ref_model(**kw).logits
+        _loss(ref_logits, tgt, doc, denom).backward()
+        ref_grads = {n: p.grad.clone() for n, p in ref_model.named_parameters()}
+
+        mesh = init_device_mesh("cpu", (world,), mesh_dim_names=("tp",))
+        tensor_parallel.apply_tp(model, mesh)
+        sd = dict(model.named_parameters())
+        assert set(sd) == set(ref_grads)                                  # FQNs unchanged by the sharding
+        lm = "language_model." if audio else ""
+        assert sd[lm + "model.layers.0.self_attn.q_proj.weight"].to_local().shape == (4 * 128 // world, 256)
+        assert sd[lm + "model.layers.0.mlp.down_proj.weight"].to_local().shape == (256, 512 // world)
+        assert sd[lm + "model.embed_tokens.weight"].to_local().shape == (384 // world, 256)
+        logits = model(**kw).logits
+        assert logits.shape == ref_logits.shape
+        _loss(logits, tgt, doc, denom).backward()
+        err_fwd = float((logits.float() - ref_logits.float())[doc > 0].abs().max()) / float(ref_logits.float().abs().max())
+        worst, worst_name = 0.0, ""
+        for n, p in model.named_parameters():
+            g = p.grad
+            g = g.full_tensor() if tensor_parallel.is_dtensor(g) else g
+            e = _rel(g.float(), ref_grads[n].float())
+            if e > worst:
+                worst, worst_name = e, n
+        q.put((rank, err_fwd, worst, worst_name))
+    finally:
+        dist.destroy_process_group()
+
+
+def _cp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import cpu_ops_shim
+        cpu_ops_shim.install()
+        from touchnet_b200 import context_parallel
+        model, text = _build(False, False)
+        B, T = 2, 256
+        kw, doc, tgt = _inputs(B, T, text.vocab_size, False)
+        denom = float((doc > 0).sum()) * text.vocab_size
+        ref_logits = model(**kw).logits
+        _loss(ref_logits, tgt, doc, denom).backward()
+        ref_grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+        model.zero_grad()
+        Tl = T // world
+        sl = slice(rank * Tl, (rank + 1) * Tl)
+        context_parallel.enable_context_parallel(model, dist.group.WORLD)
+        lg = model(**{k: v[:, sl].contiguous() for k, v in kw.items()}).logits
+        _loss(lg, tgt[:, sl], doc[:, sl], denom).backward()
+        err_fwd = float((lg.float() - ref_logits[:, sl].float()).abs().max()) / float(ref_logits.float().abs().max())
+        worst, worst_name = 0.0, ""
+        for n, p in model.named_parameters():
+            g = p.grad.clone()
+            dist.all_reduce(g)                       # every rank holds the partial sum over its tokens
+            e = _rel(g.float(), ref_grads[n].float())
+            if e > worst:
+                worst, worst_name = e, n
+        q.put((rank, err_fwd, worst, worst_name))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(target, args, port_base):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = port_base + (os.getpid() % 150)
+    procs = [ctx.Process(target=target, args=(r, 2, port) + args + (q,)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = []
+    try:
+        for _ in range(2):
+            res.append(q.get(timeout=120))
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    return sorted(res)
+
+
+@pytest.mark.parametrize("audio,bias", [(False, False), (True, True)])
+def test_tensor_parallel_matches_unsharded(audio, bias):
+    for rank, err_fwd, worst, name in _run(_tp_worker, (audio, bias), 29700):
+        assert err_fwd < 2e-2, (rank, err_fwd)       # bf16 rounding of partial sums before the reduce-scatter
+        assert worst < 3e-2, (rank, name, worst)
+
+
+def test_context_parallel_matches_unsharded():
+    for rank, err_fwd, worst, name in _run(_cp_worker, (), 29860):
+        assert err_fwd < 1e-2, (rank, err_fwd)
+        assert worst < 3e-2, (rank, name, worst)

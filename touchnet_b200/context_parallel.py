@@ -47,7 +47,7 @@ def _gather_seq(x: torch.Tensor, B: int, group) -> torch.Tensor:
     cp = dist.get_world_size(group)
     Tl = x.shape[0] // B
     xs = x.contiguous()
-    out = torch.empty((cp,) + tuple(xs.shape), dtype=xs.dtype, device=xs.device)
+    out = torch.empty((cp * xs.shape[0],) + tuple(xs.shape[1:]), dtype=xs.dtype, device=xs.device)
     dist.all_gather_into_tensor(out, xs, group=group)
     return out.view(cp, B, Tl, -1).permute(1, 0, 2, 3).reshape(B * cp * Tl, -1)
 
@@ -57,8 +57,8 @@ def _reduce_scatter_seq(x: torch.Tensor, B: int, group) -> torch.Tensor:
     cp = dist.get_world_size(group)
     T = x.shape[0] // B
     Tl = T // cp
-    xs = x.view(B, cp, Tl, -1).permute(1, 0, 2, 3).contiguous().float()
-    out = torch.empty((B, Tl, xs.shape[-1]), dtype=torch.float32, device=x.device)
+    xs = x.view(B, cp, Tl, -1).permute(1, 0, 2, 3).contiguous().float().view(cp * B * Tl, -1)
+    out = torch.empty((B * Tl, xs.shape[-1]), dtype=torch.float32, device=x.device)
     dist.reduce_scatter_tensor(out, xs, op=dist.ReduceOp.SUM, group=group)
     return out.view(B * Tl, -1).to(x.dtype)
 

@@ -110,7 +110,11 @@ class B200RMSNorm(nn.Module):
         self.variance_epsilon = eps
 
     def forward(self, x):
-        return ops.rms_norm(x, self.weight, self.variance_epsilon)
+        w = self.weight
+        if ops._is_dtensor(w):      # tensor parallel: replicated weight, sequence-sharded rows (SequenceParallel in the ref plan)
+            from . import tensor_parallel
+            w = tensor_parallel.replicated_param(w, w.device_mesh.get_group())
+        return ops.rms_norm(x, w, self.variance_epsilon)
 
 
 class B200Attention(nn.Module):
@@ -149,11 +153,21 @@ class B200DecoderLayer(nn.Module):
 
     def forward(self, hidden_states, cos, sin, plan):
         a, m = self.self_attn, self.mlp
+        if plan.tp is None:
+            return ops.decoder_layer(
+                hidden_states, self.input_layernorm.weight, a.q_proj.weight, a.k_proj.weight, a.v_proj.weight,
+                a.q_proj.bias, a.k_proj.bias, a.v_proj.bias, a.o_proj.weight, self.post_attention_layernorm.weight,
+                m.gate_proj.weight, m.up_proj.weight, m.down_proj.weight, cos, sin, plan, a.num_heads,
+                a.num_key_value_heads, self.input_layernorm.variance_epsilon)
+        # tensor parallel (tensor_parallel.py): this rank's weight shards, H/tp and KV/tp heads
+        from .tensor_parallel import local
+        wq, wk = local(a.q_proj.weight), local(a.k_proj.weight)
         return ops.decoder_layer(
-            hidden_states, self.input_layernorm.weight, a.q_proj.weight, a.k_proj.weight, a.v_proj.weight,
-            a.q_proj.bias, a.k_proj.bias, a.v_proj.bias, a.o_proj.weight, self.post_attention_layernorm.weight,
-            m.gate_proj.weight, m.up_proj.weight, m.down_proj.weight, cos, sin, plan, a.num_heads,
-            a.num_key_value_heads, self.input_layernorm.variance_epsilon)
+            hidden_states, local(self.input_layernorm.weight), wq, wk, local(a.v_proj.weight),
+            local(a.q_proj.bias), local(a.k_proj.bias), local(a.v_proj.bias), local(a.o_proj.weight),
+            local(self.post_attention_layernorm.weight), local(m.gate_proj.weight), local(m.up_proj.weight),
+            local(m.down_proj.weight), cos, sin, plan, wq.shape[0] // a.head_dim, wk.shape[0] // a.head_dim,
+            self.input_layernorm.variance_epsilon)
 
 
 class B200LlamaModel(nn.Module):
@@ -176,6 +190,10 @@ class B200LlamaModel(nn.Module):
         `attention_mask` carries document ids (ref: touchnet/models/llama/processing_llama.py:37-40)."""
         B, T, _ = inputs_embeds.shape
         dev = inputs_embeds.device
+        tp_group = getattr(self, "tp_group", None)
+        if tp_group is not None:        # inputs_embeds is this rank's sequence shard; masks / positions are the full [B, T]
+            import torch.distributed as dist
+            T = T * dist.get_world_size(tp_group)
         if position_ids is None:
             if getattr(self, "cp_group", None) is not None:
                 raise TouchNetB200Error("context parallelism needs the (sharded) position_ids of the packed batch")
@@ -190,6 +208,11 @@ class B200LlamaModel(nn.Module):
             plan = context_parallel.make_cp_plan(attention_mask, cp_group)
         else:
             plan = ops.AttnPlan(attention_mask)             # once per step, shared by all layers
+        if tp_group is not None:
+            from . import tensor_parallel
+            if attention_mask.shape[1] != T or position_ids.shape[1] != T:
+                raise TouchNetB200Error("tensor parallelism: attention_mask / position_ids must cover the whole sequence")
+            plan.tp = tensor_parallel.TPContext(tp_group, B)
         cos, sin = self.rotary_emb(position_ids)            # once per step
         x = inputs_embeds
         if x.dtype != torch.bfloat16:
@@ -283,12 +306,22 @@ class B200LlamaForCausalLM(nn.Module):
                 inputs_embeds: Optional[torch.Tensor] = None, labels=None, use_cache=None, **kwargs: Any):
         assert labels is None, "loss is computed in the train loop (ref: modeling_touch_audio.py:121)"
         ops.begin_forward(self)             # side-stream casts of stale fp32 master weights / new cache epoch under FSDP2
+        tp_group = getattr(self, "tp_group", None)
         if inputs_embeds is None:
             if input_ids is None:
                 raise TouchNetB200Error("either input_ids or inputs_embeds is required")
-            inputs_embeds = _EmbedAddFn.apply(input_ids, self.model.embed_tokens.weight, None, None)
+            if tp_group is None:
+                inputs_embeds = _EmbedAddFn.apply(input_ids, self.model.embed_tokens.weight, None, None)
+            else:
+                from . import tensor_parallel
+                inputs_embeds = tensor_parallel.embed(input_ids, self.model.embed_tokens.weight,
+                                                      tensor_parallel.TPContext(tp_group, input_ids.shape[0]))
         h = self.model(inputs_embeds, attention_mask, position_ids)
-        logits = ops.linear(h, self.lm_head.weight)
+        if tp_group is None:
+            logits = ops.linear(h, self.lm_head.weight)
+        else:       # h is the sequence shard; logits come back replicated [B, T, V]
+            from . import tensor_parallel
+            logits = tensor_parallel.lm_head(h, self.lm_head.weight, tensor_parallel.TPContext(tp_group, h.shape[0]))
         out = CausalLMOutputWithPast(logits=logits)
         return out
 
@@ -356,6 +389,19 @@ class B200TouchAudioForCausalLM(nn.Module):
                 logits_to_keep=0, check_nan: bool = False, **kwargs: Any):
         assert labels is None  # we calculate loss in train-loop (ref: modeling_touch_audio.py:121)
         ops.begin_forward(self)             # projector, decoder layers, lm_head: casts overlap the GEMMs in front of them
+        tp_group = getattr(self, "tp_group", None)
+        if inputs_embeds is None and tp_group is not None:
+            # tensor parallel: vocabulary-sharded lookup reduce-scattered onto sequence shards; the (replicated) projector
+            # runs on this rank's rows only, so its gradient is a partial sum over tp -> all-reduced
+            from . import tensor_parallel
+            tp = tensor_parallel.TPContext(tp_group, input_ids.shape[0])
+            inputs_embeds = tensor_parallel.embed(input_ids, self.language_model.model.embed_tokens.weight, tp)
+            if input_features is not None and input_ids.shape[1] != 1:
+                feats = tp.seq_slice(input_features)
+                feats = feats if feats.dtype == torch.bfloat16 else feats.to(torch.bfloat16)
+                wp = tensor_parallel.replicated_param(self.projector.weight, tp_group)
+                inputs_embeds = inputs_embeds + ops.linear(feats.contiguous(), wp)
+            self._nan_flag.add_(torch.isnan(inputs_embeds).any().to(torch.int32))
         if inputs_embeds is None:
             lm = self.language_model
             proj = None

@@ -313,6 +313,7 @@ class AttnPlan:
         self.Tq = self.T if Tq is None else int(Tq)
         self.q_blk_off = int(q_blk_off)
         self.cp_group = None
+        self.tp = None            # tensor_parallel.TPContext when the block runs tensor + sequence parallel
         self.doc = doc_ids.to(torch.int32).contiguous()
         n_ints = int(_lib.load().tn_attn_meta_ints(self.B, self.T))
         self.meta = torch.empty(n_ints, dtype=torch.int32, device=doc_ids.device)
@@ -516,10 +517,15 @@ class DecoderLayerFn(torch.autograd.Function):
                 plan, H, KV, eps):
         x2 = _rows2d(x)
         scale = 1.0 / math.sqrt(128)
+        tp = plan.tp                # tensor + sequence parallel: x holds T/tp rows, weights are this rank's shards
+        if tp is not None and plan.cp_group is not None:
+            raise _lib.TouchNetB200Error("tensor parallelism and context parallelism cannot be combined in one block")
         h1, _, rstd1 = rmsnorm_fwd(x2, ln1, eps)
+        if tp is not None:
+            h1 = tp.ag(h1)                                                   # [B*T, d]: every row, for the local heads
         nq, nkv = wq.shape[0], wk.shape[0]
-        rope_in_gemm = qkv_fusable(x2.shape[0], nq, nkv) and bq is None     # RoPE in the QKV GEMM epilogue
-        if qkv_fusable(x2.shape[0], nq, nkv):
+        rope_in_gemm = qkv_fusable(h1.shape[0], nq, nkv) and bq is None     # RoPE in the QKV GEMM epilogue
+        if qkv_fusable(h1.shape[0], nq, nkv):
             qkv = gemm_qkv_fwd(h1, wqb, wkb, wvb, rope=(cos, sin) if rope_in_gemm else None)
             q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
         else:
@@ -534,10 +540,18 @@ class DecoderLayerFn(torch.autograd.Function):
         else:   # context parallel: K/V of all cp ranks are gathered, the kernel runs on this rank's query window
             from . import context_parallel as _cp
             o, lse, k, v = _cp.cp_attn_fwd(q, k, v, plan, H, KV, scale)
-        x1 = gemm(o, wob, residual=x2)
+        if tp is None:
+            x1 = gemm(o, wob, residual=x2)
+        else:                                                                # partial sums over tp -> this rank's rows
+            x1 = tp.rs(gemm(o, wob)).add_(x2)
         h2, _, rstd2 = rmsnorm_fwd(x1, ln2, eps)
+        if tp is not None:
+            h2 = tp.ag(h2)
         g, u, hm = gemm_swiglu(h2, wgb, wub)
-        out = gemm(hm, wdb, residual=x1)
+        if tp is None:
+            out = gemm(hm, wdb, residual=x1)
+        else:
+            out = tp.rs(gemm(hm, wdb)).add_(x1)
         ctx.save_for_backward(x2, ln1, ln2, wqb, wkb, wvb, wob, wgb, wub, wdb, cos, sin, rstd1, h1, q, k, v, o, lse, x1,
                               rstd2, h2, g, u, hm)
         ctx.plan, ctx.H, ctx.KV, ctx.scale, ctx.has_bias = plan, H, KV, scale, bq is not None
@@ -550,12 +564,15 @@ class DecoderLayerFn(torch.autograd.Function):
         (x2, ln1, ln2, wqb, wkb, wvb, wob, wgb, wub, wdb, cos, sin, rstd1, h1, q, k, v, o, lse, x1, rstd2, h2, g, u,
          hm) = ctx.saved_tensors
         H, KV, f32 = ctx.H, ctx.KV, ctx.f32
+        tp = ctx.plan.tp
         d2 = _rows2d(dout)
         if d2.dtype != BF16:
             d2 = d2.to(BF16)
         # ---- MLP ----
-        dhm = gemm(d2, wdb, b_mn=True)
-        dwd = _wgrad(d2, hm, f32)
+        d2f = d2 if tp is None else tp.ag(d2)          # backward of the forward reduce-scatter
+        dhm = gemm(d2f, wdb, b_mn=True)
+        dwd = _wgrad(d2f, hm, f32)
+        del d2f
         dg, du = swiglu_bwd(g, u, dhm)
         del dhm
         dh2 = gemm(dg, wgb, b_mn=True)
@@ -563,12 +580,16 @@ class DecoderLayerFn(torch.autograd.Function):
         dwg = _wgrad(dg, h2, f32)
         dwu = _wgrad(du, h2, f32)
         del dg, du
+        if tp is not None:
+            dh2 = tp.rs(dh2)                           # backward of the forward all-gather
         dx1, dln2 = rmsnorm_bwd(x1, dh2, ln2, rstd2, ds_extra=d2)
         # ---- attention ----
-        do = gemm(dx1, wob, b_mn=True)
-        dwo = _wgrad(dx1, o, f32)
+        dx1f = dx1 if tp is None else tp.ag(dx1)
+        do = gemm(dx1f, wob, b_mn=True)
+        dwo = _wgrad(dx1f, o, f32)
+        del dx1f
         nq, nkv = wqb.shape[0], wkb.shape[0]
-        fused = qkv_fusable(x2.shape[0], nq, nkv)
+        fused = qkv_fusable(h1.shape[0], nq, nkv)
         if ctx.plan.cp_group is not None:
             from . import context_parallel as _cp
             dq, dk, dv = _cp.cp_attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale)   # dK/dV reduce-scattered
@@ -578,7 +599,7 @@ class DecoderLayerFn(torch.autograd.Function):
             rope_apply_(dq, cos, sin, H, 128, inverse=True)
             rope_apply_(dk, cos, sin, KV, 128, inverse=True)
         elif fused:   # inverse RoPE happens in the attention-backward epilogues
-            dqkv = torch.empty((x2.shape[0], nq + 2 * nkv), dtype=BF16, device=x2.device)
+            dqkv = torch.empty((h1.shape[0], nq + 2 * nkv), dtype=BF16, device=x2.device)
             dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
             attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale, out=(dq, dk, dv), rope=(cos, sin))
         else:
@@ -594,7 +615,12 @@ class DecoderLayerFn(torch.autograd.Function):
         dbq = dbk = dbv = None
         if ctx.has_bias:
             dbq = dq.float().sum(0).to(ctx.w_dtype); dbk = dk.float().sum(0).to(ctx.w_dtype); dbv = dv.float().sum(0).to(ctx.w_dtype)
+        if tp is not None:
+            dh1 = tp.rs(dh1)
         dx, dln1 = rmsnorm_bwd(x2, dh1, ln1, rstd1, ds_extra=dx1)
+        if tp is not None:                             # replicated norm weights, sequence-sharded rows: sum the partials
+            tp.all_reduce_(dln1)
+            tp.all_reduce_(dln2)
         return (dx.view(dout.shape), dln1.to(ln1.dtype), dwq, dwk, dwv, dbq, dbk, dbv, dwo, dln2.to(ln2.dtype), dwg, dwu,
                 dwd) + (None,) * 13
 

@@ -151,17 +151,102 @@ def _cp_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def _run(target, args, port_base):
+def _tp_fsdp_worker(rank, world, port, q):
+    """TP=2 x FSDP2=2 (BASELINE config 5 at a quarter of the mesh): 2-D DTensor parameters, each dp rank its own row."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import cpu_ops_shim
+        cpu_ops_shim.install()
+        from torch.distributed.device_mesh import init_device_mesh
+        from torch.distributed.fsdp import fully_shard
+        from touchnet_b200 import tensor_parallel
+        model, text = _build(False, False)
+        B, T = 2, 256
+        kw, doc, tgt = _inputs(B, T, text.vocab_size, False)
+        denom = float((doc > 0).sum()) * text.vocab_size
+        ref_model = copy.deepcopy(model)
+        ref_logits = ref_model(**kw).logits
+        _loss(ref_logits, tgt, doc, denom).backward()
+        ref_grads = {n: p.grad.clone() for n, p in ref_model.named_parameters()}
+
+        # through the TrainSpec parallelize_fn (touchnet_b200/parallelize.py), as touchnet/bin/train.py:184-190 calls it
+        from touchnet_b200 import parallelize
+        mesh = init_device_mesh("cpu", (2, 2), mesh_dim_names=("dp_shard_cp", "tp"))
+        dims = _Cfg(tp_enabled=True, cp_enabled=False, pp_enabled=False, dp_shard_enabled=True, dp_replicate_enabled=False)
+        job = _Cfg(training_mixed_precision_param="float32", training_mixed_precision_reduce="float32",
+                   training_fsdp_reshard_after_forward="default")
+        model = parallelize.make_parallelize_fn(None)(model, mesh, dims, job)
+        d = mesh["dp_shard_cp"].get_local_rank()
+        row = slice(d, d + 1)
+        logits = model(**{k: v[row] for k, v in kw.items()}).logits
+        _loss(logits, tgt[row], doc[row], denom).backward()
+        err_fwd = float((logits.float() - ref_logits[row].float())[doc[row] > 0].abs().max()) / float(ref_logits.float().abs().max())
+        worst, worst_name = 0.0, ""
+        for n, p in model.named_parameters():
+            g = p.grad.full_tensor() * 2                                   # FSDP averages over dp; rank losses are partial sums
+            e = _rel(g.float(), ref_grads[n].float())
+            if e > worst:
+                worst, worst_name = e, n
+        q.put((rank, err_fwd, worst, worst_name))
+    finally:
+        dist.destroy_process_group()
+
+
+def _cp_fsdp_worker(rank, world, port, q):
+    """CP=2 x FSDP2 over the flattened dp_shard_cp mesh of 4 (BASELINE config 4 at half the mesh;
+    ref: touchnet/utils/distributed.py:116-157 builds the same flattened mesh for apply_fsdp)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import cpu_ops_shim
+        cpu_ops_shim.install()
+        from torch.distributed.device_mesh import init_device_mesh
+        from torch.distributed.fsdp import fully_shard
+        from touchnet_b200 import context_parallel
+        model, text = _build(False, False)
+        B, T = 2, 256
+        kw, doc, tgt = _inputs(B, T, text.vocab_size, False)
+        denom = float((doc > 0).sum()) * text.vocab_size
+        ref_model = copy.deepcopy(model)
+        ref_logits = ref_model(**kw).logits
+        _loss(ref_logits, tgt, doc, denom).backward()
+        ref_grads = {n: p.grad.clone() for n, p in ref_model.named_parameters()}
+
+        mesh = init_device_mesh("cpu", (2, 2), mesh_dim_names=("dp_shard", "cp"))
+        flat = mesh["dp_shard", "cp"]._flatten("dp_shard_cp")
+        context_parallel.enable_context_parallel(model, mesh["cp"].get_group())
+        for layer in model.model.layers:
+            fully_shard(layer, mesh=flat)
+        fully_shard(model, mesh=flat)
+        d, c = mesh["dp_shard"].get_local_rank(), mesh["cp"].get_local_rank()
+        Tl = T // 2
+        row, sl = slice(d, d + 1), slice(c * Tl, (c + 1) * Tl)
+        logits = model(**{k: v[row, sl].contiguous() for k, v in kw.items()}).logits
+        _loss(logits, tgt[row, sl], doc[row, sl], denom).backward()
+        err_fwd = float((logits.float() - ref_logits[row, sl].float()).abs().max()) / float(ref_logits.float().abs().max())
+        worst, worst_name = 0.0, ""
+        for n, p in model.named_parameters():
+            g = p.grad.full_tensor() * 4                                   # FSDP averages over the 4 ranks' partial sums
+            e = _rel(g.float(), ref_grads[n].float())
+            if e > worst:
+                worst, worst_name = e, n
+        q.put((rank, err_fwd, worst, worst_name))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(target, args, port_base, world=2):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = port_base + (os.getpid() % 150)
-    procs = [ctx.Process(target=target, args=(r, 2, port) + args + (q,)) for r in range(2)]
+    procs = [ctx.Process(target=target, args=(r, world, port) + args + (q,)) for r in range(world)]
     for p in procs:
         p.start()
     res = []
     try:
-        for _ in range(2):
-            res.append(q.get(timeout=120))
+        for _ in range(world):
+            res.append(q.get(timeout=180))
     finally:
         for p in procs:
             p.join(timeout=60)
@@ -178,5 +263,17 @@ def test_tensor_parallel_matches_unsharded(audio, bias):
 
 def test_context_parallel_matches_unsharded():
     for rank, err_fwd, worst, name in _run(_cp_worker, (), 29860):
+        assert err_fwd < 1e-2, (rank, err_fwd)
+        assert worst < 3e-2, (rank, name, worst)
+
+
+def test_tensor_parallel_composes_with_fsdp2():
+    for rank, err_fwd, worst, name in _run(_tp_fsdp_worker, (), 30020, world=4):
+        assert err_fwd < 2e-2, (rank, err_fwd)
+        assert worst < 3e-2, (rank, name, worst)
+
+
+def test_context_parallel_composes_with_fsdp2():
+    for rank, err_fwd, worst, name in _run(_cp_fsdp_worker, (), 30180, world=4):
         assert err_fwd < 1e-2, (rank, err_fwd)
         assert worst < 3e-2, (rank, name, worst)

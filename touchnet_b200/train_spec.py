@@ -4,8 +4,9 @@ Two seams:
 
 1. Outer plugin API - `TrainSpec` (ref: touchnet/utils/train_spec.py:25-62).  `register()` clones the reference's own
    "llama" / "touch_audio" specs (ref: touchnet/__init__.py:35-117) and swaps `model_cls` for the B200 modules under the
-   names "llama_b200" / "touch_audio_b200"; every other callable (parallelize_fn, dataloader, optimizer, loss, flops ...)
-   stays the reference's.  `--training_model_name touch_audio_b200` then selects it (ref: touchnet/bin/train.py:119).
+   names "llama_b200" / "touch_audio_b200"; `parallelize_fn` is wrapped (parallelize.py: tensor / context parallelism
+   are applied to the fused block, FSDP2 / AC stay the reference's); every other callable (dataloader, optimizer, loss,
+   flops ...) stays the reference's.  `--training_model_name touch_audio_b200` then selects it (ref: touchnet/bin/train.py:119).
 
 2. Inner operator API - HF's attention-interface registry
    (`ALL_ATTENTION_FUNCTIONS[config._attn_implementation]`, hf: models/llama/modeling_llama.py:272-286;
@@ -23,7 +24,7 @@ from typing import Any, Callable, Optional
 
 import torch
 
-from . import modeling, ops
+from . import modeling, ops, parallelize
 
 _tls = threading.local()
 
@@ -78,7 +79,9 @@ def register(touchnet_pkg=None) -> list[str]:
             import touchnet as touchnet_pkg  # type: ignore
         from touchnet.utils.train_spec import get_train_spec, register_train_spec  # type: ignore
         for base, cls in (("llama", modeling.B200LlamaForCausalLM), ("touch_audio", modeling.B200TouchAudioForCausalLM)):
-            spec = dataclasses.replace(get_train_spec(base), name=base + "_b200", model_cls=cls)
+            ref_spec = get_train_spec(base)
+            spec = dataclasses.replace(ref_spec, name=base + "_b200", model_cls=cls,
+                                       parallelize_fn=parallelize.make_parallelize_fn(ref_spec.parallelize_fn))
             try:
                 register_train_spec(spec)
             except ValueError:
@@ -88,6 +91,7 @@ def register(touchnet_pkg=None) -> list[str]:
     except Exception:
         for base, cls in (("llama", modeling.B200LlamaForCausalLM), ("touch_audio", modeling.B200TouchAudioForCausalLM)):
             spec = TrainSpec(name=base + "_b200", model_cls=cls, config_cls=None,
+                             parallelize_fn=parallelize.make_parallelize_fn(None),
                              get_num_flop_per_token_fn=get_num_flop_per_token, get_num_params_fn=get_num_params)
             _local_specs[spec.name] = spec
             names.append(spec.name)

@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--seq-len", type=int, default=8192)
     ap.add_argument("--batch", type=int, default=1, help="packed rows per GPU")
     ap.add_argument("--layers", type=int, default=32, help="debug only: anything but 32 is not the named workload")
+    ap.add_argument("--tp", type=int, default=1, help="tensor-parallel degree (BASELINE config 5); default mesh is pure FSDP2")
+    ap.add_argument("--cp", type=int, default=1, help="context-parallel degree (BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -110,13 +112,19 @@ def h2d_bytes(host: dict) -> int:
     return int(sum(v.numel() * v.element_size() for v in host.values()))
 
 
-def run_step(model, d: dict, meta: dict, B: int, T: int):
-    """frontend -> forward -> pack loss -> backward.  Returns the loss tensor (device)."""
+def run_step(model, d: dict, meta: dict, B: int, T: int, cp_slice=None):
+    """frontend -> forward -> pack loss -> backward.  Returns the loss tensor (device).
+    cp_slice: this rank's sequence window under context parallelism (every per-token buffer is cut to it, as the
+    reference's create_context_parallel_ctx does, ref: touchnet/bin/train.py:363-387)."""
     from touchnet_b200 import frontend
     feats = torch.zeros((B * T, MEL * STACK), dtype=torch.float32, device=d["wav"].device)
     fb, frames = frontend.fbank_batch(d["wav"], meta["lens"], num_mel_bins=MEL)
     frontend.stack_batch(fb, frames, STACK, STRIDE, True, into=feats, dst_rows=meta["dst_rows"])
-    out = model(input_ids=d["input_ids"], input_features=feats.view(B, T, -1), attention_mask=d["attention_mask"],
+    feats = feats.view(B, T, -1)
+    if cp_slice is not None:
+        feats = feats[:, cp_slice].contiguous()
+        d = {k: (v[:, cp_slice].contiguous() if v.dim() == 2 and v.shape[1] == T else v) for k, v in d.items()}
+    out = model(input_ids=d["input_ids"], input_features=feats, attention_mask=d["attention_mask"],
                 position_ids=d["position_ids"])
     # pack loss next to the path (ref: touchnet/loss/cross_entropy.py:12-50), fused CUDA (csrc/loss.cu)
     from touchnet_b200 import loss as tn_loss
@@ -325,8 +333,12 @@ def workload_config(args, n):
                         f"ffn=14336 V=128256, projector {MEL * STACK}->4096), audio+text packed rows, fbank80 stack{STACK}/"
                         f"stride{STRIDE} frontend on GPU, fwd+bwd, fp32 master weights + fp32 weight grads",
             "global_batch": args.batch * n, "seq_len": args.seq_len,
-            "parallelism": "single GPU" if n == 1 else f"FSDP2 dp_shard={n} (bf16 params / fp32 reduce), "
-                           f"{os.environ.get('TN_SM_MARGIN', '0')} SMs left to NCCL",
+            "parallelism": "single GPU" if n == 1 else
+                           f"FSDP2 dp_shard={n // (args.tp * args.cp)} (bf16 params / fp32 reduce, reshard policy "
+                           f"{'default' if os.environ.get('TN_FSDP_RESHARD', '0') != '0' else 'never'})"
+                           + (f" x TP={args.tp} (+sequence parallel)" if args.tp > 1 else "")
+                           + (f" x CP={args.cp} (K/V all-gather, exact document mask)" if args.cp > 1 else "")
+                           + f", {os.environ.get('TN_SM_MARGIN', '0')} SMs left to NCCL",
             "l2_policy": "inputs larger than L2: every step streams >16 GB of weights through a 126 MB L2"}
 
 
@@ -367,10 +379,25 @@ def main():
         for p in model.parameters():
             if p.dim() == 2:
                 p.normal_(0.0, 0.02)
+    tp, cp = args.tp, args.cp
+    assert world % (tp * cp) == 0, f"--tp {tp} x --cp {cp} must divide {world} GPUs"
+    dp = world // (tp * cp)
+    cp_slice = None
     if world > 1:
         from torch.distributed.fsdp import MixedPrecisionPolicy, fully_shard
         from torch.distributed.device_mesh import init_device_mesh
-        mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("dp_shard",))
+        # mesh order of the reference: dp_shard outermost, then cp, tp innermost (touchnet/utils/distributed.py:116-157)
+        full_mesh = init_device_mesh("cuda", (dp, cp, tp), mesh_dim_names=("dp_shard", "cp", "tp"))
+        if tp > 1:
+            from touchnet_b200 import tensor_parallel
+            tensor_parallel.apply_tp(model, full_mesh["tp"])
+        if cp > 1:
+            from touchnet_b200 import context_parallel
+            context_parallel.enable_context_parallel(model, full_mesh["cp"].get_group())
+            c = full_mesh["cp"].get_local_rank()
+            cp_slice = slice(c * (T // cp), (c + 1) * (T // cp))
+        mesh = full_mesh["dp_shard", "cp"]._flatten("dp_shard_cp") if cp > 1 else full_mesh["dp_shard"]
+    if world > 1 and mesh.size() > 1:
         mp = MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.float32)
         layers = model.language_model.model.layers       # ref: touchnet/models/helper_func.py:134-202 apply_fsdp
         # reshard policy "never" of the reference (training_fsdp_reshard_after_forward, helper_func.py:141-186): the bf16
@@ -387,7 +414,7 @@ def main():
                 layer.set_modules_to_backward_prefetch(list(reversed(layers[max(0, i - depth):i])))
     model.train()
 
-    host, meta = make_host_batch(dist_util_seed(2025, rank), B, T, cfg.text_config.vocab_size)
+    host, meta = make_host_batch(dist_util_seed(2025, rank // (tp * cp)), B, T, cfg.text_config.vocab_size)  # dp coordinate
     resident = to_device(host, dev)
     torch.cuda.synchronize()
 
@@ -399,7 +426,7 @@ def main():
     def one_step(inputs):
         model.zero_grad(set_to_none=True)
         ops.invalidate_bf16_cache(model)     # the fp32->bf16 weight cast is part of every step
-        return run_step(model, inputs, meta, B, T)
+        return run_step(model, inputs, meta, B, T, cp_slice)
 
     # ---------------- device-resident arm ----------------
     for _ in range(max(args.warmup, 3)):
@@ -424,8 +451,8 @@ def main():
     gemm_ms, gemm_flops, gemm_n = gt.summary()
     from touchnet_b200 import dist_util
     ms = dist_util.max_over_ranks(ms, dev)
-    tokens_per_step = B * T * world
-    value = dist_util.whole_job_tokens_per_s(B * T, args.steps, world, ms)
+    tokens_per_step = B * T * dp                     # tp / cp ranks share their rows
+    value = dist_util.whole_job_tokens_per_s(B * T, args.steps, dp, ms)
     final_loss = float(loss.item())
 
     # ---------------- end-to-end arm: pinned host inputs, H2D inside, loss read back every step ----------------

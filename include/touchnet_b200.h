@@ -188,6 +188,24 @@ int tn_pack_ce_bwd_bf16(void* logits, int64_t ld, const int64_t* labels, const i
 int tn_bestrq_tokenize_f32(const float* feats, int64_t ld, const float* proj, const float* codebook, int64_t T, int D,
                            int E, int V, int32_t* codes, tn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Optimizer step next to the path, on the rank-local fp32 shards.
+ *   tn_sumsq_f32: partials[0..*n_partials_used) = block-wise sums of x[i]^2 (deterministic; the caller adds them up, sums
+ *     over tensors / ranks and takes the root) - replaces torch.nn.utils.get_total_norm in
+ *     touchnet/utils/distributed.py:426-491.  `partials` holds tn_sumsq_num_partials() floats.
+ *   tn_scale_f32: x *= scale[0] (device scalar, no-op when it is 1) - clip_grads_with_norm_ of the same function.
+ *   tn_adamw_f32: one AdamW step (decoupled weight decay, bias corrections passed in) replacing
+ *     torch.optim.AdamW(..., fused=True) as built by touchnet/utils/optimizer.py:127-172; `grad_scale` (device scalar or
+ *     NULL) multiplies the gradient on the fly (the clip coefficient, so clipping needs no pass of its own) and
+ *     `param_bf16` (or NULL) receives the bf16 working copy of the updated parameter.
+ */
+int tn_sumsq_num_partials(void);
+int tn_sumsq_f32(const float* x, int64_t n, float* partials, int* n_partials_used, tn_stream_t stream);
+int tn_scale_f32(float* x, int64_t n, const float* scale, tn_stream_t stream);
+int tn_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                 float bias_correction2_sqrt, const float* grad_scale, tn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

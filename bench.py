@@ -40,30 +40,53 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seq-len", type=int, default=8192)
-    ap.add_argument("--batch", type=int, default=1, help="packed rows per GPU")
+    ap.add_argument("--workload", default="llama3_8b_asr", choices=sorted(WORKLOADS),
+                    help="llama3_8b_asr = the configuration the metric is quoted on (default); qwen2_audio_7b_asr = "
+                         "BASELINE config 3 (MHA + q/k/v bias, V=156032, stack 13 / stride 12), a full-size smoke case")
+    ap.add_argument("--seq-len", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None, help="packed rows per GPU")
     ap.add_argument("--layers", type=int, default=32, help="debug only: anything but 32 is not the named workload")
     ap.add_argument("--tp", type=int, default=1, help="tensor-parallel degree (BASELINE config 5); default mesh is pure FSDP2")
     ap.add_argument("--cp", type=int, default=1, help="context-parallel degree (BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    select_workload(args)
+    return args
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------------
 STACK, STRIDE, MEL = 5, 4, 80          # audio pretrain recipe (examples/audio/pretrain/wenetspeech/run.sh:57)
+WORKLOADS = {
+    # BASELINE config 2/5 model around the audio projector: the configuration the metric is quoted on
+    "llama3_8b_asr": dict(stack=5, stride=4, seq_len=8192, batch=1, name="Llama-3-8B-ASR", text=dict(
+        hidden_size=4096, intermediate_size=14336, num_attention_heads=32, num_key_value_heads=8, vocab_size=128256,
+        rope_theta=500000.0, attention_bias=False, model_type="llama",
+        rope_scaling={"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                      "original_max_position_embeddings": 8192})),
+    # BASELINE config 3: Qwen2-Audio-7B init shape (examples/audio/sft/asr/wenetspeech/config/Qwen2-Audio-7B.json:27-51)
+    "qwen2_audio_7b_asr": dict(stack=13, stride=12, seq_len=4096, batch=2, name="Qwen2-Audio-7B-shaped ASR", text=dict(
+        hidden_size=4096, intermediate_size=11008, num_attention_heads=32, num_key_value_heads=32, vocab_size=156032,
+        rope_theta=10000.0, attention_bias=True, model_type="qwen2", rope_scaling=None)),
+}
+_W = WORKLOADS["llama3_8b_asr"]
+
+
+def select_workload(args):
+    global STACK, STRIDE, _W
+    _W = WORKLOADS[args.workload]
+    STACK, STRIDE = _W["stack"], _W["stride"]
+    args.seq_len = args.seq_len or _W["seq_len"]
+    args.batch = args.batch or _W["batch"]
 
 
 def text_config(layers: int):
-    """Llama-3-8B shape (L=32, d=4096, H=32, KV=8, hd=128, ffn=14336, V=128256, theta 5e5 + llama3 scaling)."""
-    return NS(hidden_size=4096, intermediate_size=14336, num_hidden_layers=layers, num_attention_heads=32,
-              num_key_value_heads=8, head_dim=128, vocab_size=128256, rms_norm_eps=1e-5, rope_theta=500000.0,
-              rope_scaling={"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
-                            "original_max_position_embeddings": 8192},
-              attention_bias=False, tie_word_embeddings=False, initializer_range=0.02, model_type="llama",
-              pad_token_id=0)
+    """Default: Llama-3-8B shape (L=32, d=4096, H=32, KV=8, hd=128, ffn=14336, V=128256, theta 5e5 + llama3
+    scaling)."""
+    return NS(num_hidden_layers=layers, head_dim=128, rms_norm_eps=1e-5, tie_word_embeddings=False,
+              initializer_range=0.02, pad_token_id=0, **_W["text"])
 
 
 def asr_config(layers: int):
@@ -272,22 +295,24 @@ def cpu_reference_setup(seed=2025):
     torch.set_num_threads(os.cpu_count() or 1)
     tc = text_config(1)
     cfg = mo.OracleConfig(hidden_size=tc.hidden_size, intermediate_size=tc.intermediate_size, num_hidden_layers=1,
-                          num_attention_heads=32, num_key_value_heads=8, head_dim=128, vocab_size=8,
+                          num_attention_heads=tc.num_attention_heads, num_key_value_heads=tc.num_key_value_heads,
+                          head_dim=128, vocab_size=8,
                           rope_theta=tc.rope_theta, rope_scaling=tc.rope_scaling)
     g = torch.Generator().manual_seed(seed)
     d, f = cfg.hidden_size, cfg.intermediate_size
     L = "model.layers.0."
-    params = {L + "self_attn.q_proj.weight": torch.randn(4096, d, generator=g) * 0.02,
-              L + "self_attn.k_proj.weight": torch.randn(1024, d, generator=g) * 0.02,
-              L + "self_attn.v_proj.weight": torch.randn(1024, d, generator=g) * 0.02,
-              L + "self_attn.o_proj.weight": torch.randn(d, 4096, generator=g) * 0.02,
+    nq, nkv = tc.num_attention_heads * 128, tc.num_key_value_heads * 128
+    params = {L + "self_attn.q_proj.weight": torch.randn(nq, d, generator=g) * 0.02,
+              L + "self_attn.k_proj.weight": torch.randn(nkv, d, generator=g) * 0.02,
+              L + "self_attn.v_proj.weight": torch.randn(nkv, d, generator=g) * 0.02,
+              L + "self_attn.o_proj.weight": torch.randn(d, nq, generator=g) * 0.02,
               L + "mlp.gate_proj.weight": torch.randn(f, d, generator=g) * 0.02,
               L + "mlp.up_proj.weight": torch.randn(f, d, generator=g) * 0.02,
               L + "mlp.down_proj.weight": torch.randn(d, f, generator=g) * 0.02,
               L + "input_layernorm.weight": torch.ones(d), L + "post_attention_layernorm.weight": torch.ones(d)}
     for p in params.values():
         p.requires_grad_(True)
-    buf, placed = batching.plan_audio_text_batch(seed, 1, CPU_SAMPLE_T, 128256, stride=STRIDE, max_s=30.0)
+    buf, placed = batching.plan_audio_text_batch(seed, 1, CPU_SAMPLE_T, tc.vocab_size, stride=STRIDE, max_s=30.0)
     doc, pos = buf["attention_mask"], buf["position_ids"]
     inv, sc = mo.rope_inv_freq(cfg)
     cos, sin = mo.rope_cos_sin(pos, inv, sc, torch.float32)
@@ -329,8 +354,11 @@ def run_reference_arm(args):
 
 
 def workload_config(args, n):
-    return {"workload": f"Llama-3-8B-ASR (TouchAudioForCausalLM, Llama-3-8B text config L={args.layers} d=4096 H=32 KV=8 "
-                        f"ffn=14336 V=128256, projector {MEL * STACK}->4096), audio+text packed rows, fbank80 stack{STACK}/"
+    t = _W["text"]
+    return {"workload": f"{_W['name']} (TouchAudioForCausalLM, text config L={args.layers} d={t['hidden_size']} "
+                        f"H={t['num_attention_heads']} KV={t['num_key_value_heads']} ffn={t['intermediate_size']} "
+                        f"V={t['vocab_size']}{' +qkv bias' if t['attention_bias'] else ''}, projector {MEL * STACK}->"
+                        f"{t['hidden_size']}), audio+text packed rows, fbank80 stack{STACK}/"
                         f"stride{STRIDE} frontend on GPU, fwd+bwd, fp32 master weights + fp32 weight grads",
             "global_batch": args.batch * n, "seq_len": args.seq_len,
             "parallelism": "single GPU" if n == 1 else

@@ -75,12 +75,13 @@ int tn_swiglu_bwd_bf16(const void* G, const void* U, const void* dH, void* dG, v
  *   fwd: if R != NULL: S = X + R (bf16, written to S_out if non-NULL) else S = X;
  *        Y = w ⊙ bf16(S · rsqrt(mean(S²)+eps));  rstd[row] (fp32) saved for backward.
  *   bwd: dS = rstd·(w⊙dY) − rstd³/d · S · Σ(w⊙dY⊙S)  (+ dS_extra if non-NULL: gradient flowing through the residual
- *        branch), dW_partial[blk, d] fp32 partial sums (caller reduces over blk; num_partials returned rows).
+ *        branch), dW_partial[num_partials, d] fp32 partial sums (workspace; num_partials = tn_rmsnorm_bwd_num_partials())
+ *        and, if dW != NULL, dW[d] = their column sums in a fixed order (a second, tiny kernel on the same stream).
  */
 int tn_rmsnorm_fwd_bf16(const void* X, const void* R, const void* w, int w_is_f32, void* S_out, void* Y, float* rstd,
                         int64_t rows, int d, float eps, tn_stream_t stream);
 int tn_rmsnorm_bwd_bf16(const void* S, const void* dY, const void* dS_extra, const void* w, int w_is_f32,
-                        const float* rstd, void* dS, float* dW_partial, int num_partials, int64_t rows, int d,
+                        const float* rstd, void* dS, float* dW_partial, int num_partials, float* dW, int64_t rows, int d,
                         tn_stream_t stream);
 int tn_rmsnorm_bwd_num_partials(void);
 

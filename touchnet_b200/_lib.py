@@ -27,7 +27,7 @@ _SIGNATURES = {
                          _vp],
     "tn_swiglu_bwd_bf16": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     "tn_rmsnorm_fwd_bf16": [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _f, _vp],
-    "tn_rmsnorm_bwd_bf16": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i64, _i, _vp],
+    "tn_rmsnorm_bwd_bf16": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i64, _i, _vp],
     "tn_rmsnorm_bwd_num_partials": [],
     "tn_rope_table": [_vp, _vp, _f, _vp, _vp, _i64, _i, _vp],
     "tn_rope_apply_bf16": [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp],
@@ -84,7 +84,7 @@ def load(path: str | None = None) -> ctypes.CDLL:
 
 
 # kernels launched per entry point (for bench.py's `gpu_launches` claim)
-_LAUNCHES = {"tn_attn_prep": 2, "tn_attn_bwd_bf16": 3, "tn_logmel_power_f32": 2}
+_LAUNCHES = {"tn_attn_prep": 2, "tn_attn_bwd_bf16": 3, "tn_logmel_power_f32": 2, "tn_rmsnorm_bwd_bf16": 2}
 launch_count = 0
 _hooks = []   # callables(name, phase) with phase in {"pre", "post"}; bench.py uses them to time kernel classes
 

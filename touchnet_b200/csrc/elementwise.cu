@@ -17,7 +17,7 @@ namespace tn {
 // ---------------------------------------------------------------------------------------------------------------
 // RMSNorm forward: one warp per row, whole row cached in registers (NV uint4 vectors per lane).
 // ---------------------------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, bool HAS_R>
 __global__ void __launch_bounds__(256, (NV <= 16) ? 2 : 1) rmsnorm_fwd_kernel(const uint4* __restrict__ X, const uint4* __restrict__ R,
                                                           const void* __restrict__ w, int w_is_f32,
                                                           uint4* __restrict__ S_out, uint4* __restrict__ Y,
@@ -28,58 +28,85 @@ __global__ void __launch_bounds__(256, (NV <= 16) ? 2 : 1) rmsnorm_fwd_kernel(co
   if (row >= rows) return;
   const uint32_t lane = lane_id();
   const uint4* x = X + row * nvec;
-  const uint4* r = R ? R + row * nvec : nullptr;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
   uint4 v[NV];
-  float ss = 0.f;
+  // all loads of the row are issued back to back (no control flow between them): NV x 16 B in flight per lane
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
-    if (c < nvec) {
-      uint4 a = x[c];
-      if (r) {
+    v[i] = (c < nvec) ? x[c] : zero4;
+  }
+  if (HAS_R) {                               // fused residual add (own instantiation; not used by the decoder block)
+    const uint4* r = R + row * nvec;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
         const uint4 b = r[c];
+        uint4 a = v[i];
         a.x = pack_bf16x2(bf16lo(a.x) + bf16lo(b.x), bf16hi(a.x) + bf16hi(b.x));
         a.y = pack_bf16x2(bf16lo(a.y) + bf16lo(b.y), bf16hi(a.y) + bf16hi(b.y));
         a.z = pack_bf16x2(bf16lo(a.z) + bf16lo(b.z), bf16hi(a.z) + bf16hi(b.z));
         a.w = pack_bf16x2(bf16lo(a.w) + bf16lo(b.w), bf16hi(a.w) + bf16hi(b.w));
         if (S_out) S_out[row * nvec + c] = a;
+        v[i] = a;
       }
-      v[i] = a;
-      const uint32_t ws[4] = {a.x, a.y, a.z, a.w};
+    }
+  }
+  float ss = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float lo = bf16lo(ws[j]), hi = bf16hi(ws[j]);
-        ss += lo * lo + hi * hi;
-      }
+  for (int i = 0; i < NV; ++i) {
+    const uint32_t ws[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = bf16lo(ws[j]), hi = bf16hi(ws[j]);
+      ss += lo * lo + hi * hi;
     }
   }
   ss = warp_sum(ss);
   const float rstd = rsqrtf(ss / float(d) + eps);
   if (lane == 0) rstd_out[row] = rstd;
+  // weight as packed bf16 pairs (fp32 master weights are rounded here, exactly what `.to(bf16)` does); the (L1/L2-resident)
+  // weight vectors are fetched in groups of G (register budget: 2 CTAs per SM), loads first, then arithmetic
+  constexpr int G = NV < 2 ? NV : 2;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nvec) {
-      float wf[8];
-      if (w_is_f32) {
-        const float4 w0 = reinterpret_cast<const float4*>(w)[2 * c], w1 = reinterpret_cast<const float4*>(w)[2 * c + 1];
-        wf[0] = bf16_round(w0.x); wf[1] = bf16_round(w0.y); wf[2] = bf16_round(w0.z); wf[3] = bf16_round(w0.w);
-        wf[4] = bf16_round(w1.x); wf[5] = bf16_round(w1.y); wf[6] = bf16_round(w1.z); wf[7] = bf16_round(w1.w);
-      } else {
-        const uint4 wb = reinterpret_cast<const uint4*>(w)[c];
-        wf[0] = bf16lo(wb.x); wf[1] = bf16hi(wb.x); wf[2] = bf16lo(wb.y); wf[3] = bf16hi(wb.y);
-        wf[4] = bf16lo(wb.z); wf[5] = bf16hi(wb.z); wf[6] = bf16lo(wb.w); wf[7] = bf16hi(wb.w);
+  for (int i0 = 0; i0 < NV; i0 += G) {
+    uint4 wp[G];
+    if (w_is_f32) {
+      float4 w0[G], w1[G];
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        const int c = lane + 32 * (i0 + k);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        w0[k] = (c < nvec) ? reinterpret_cast<const float4*>(w)[2 * c] : z;
+        w1[k] = (c < nvec) ? reinterpret_cast<const float4*>(w)[2 * c + 1] : z;
       }
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+        wp[k] = make_uint4(pack_bf16x2(w0[k].x, w0[k].y), pack_bf16x2(w0[k].z, w0[k].w), pack_bf16x2(w1[k].x, w1[k].y),
+                           pack_bf16x2(w1[k].z, w1[k].w));
+    } else {
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        const int c = lane + 32 * (i0 + k);
+        wp[k] = (c < nvec) ? reinterpret_cast<const uint4*>(w)[c] : zero4;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int i = i0 + k;
+      const int c = lane + 32 * i;
       const uint32_t ws[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      const uint32_t wq[4] = {wp[k].x, wp[k].y, wp[k].z, wp[k].w};
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        // reference: (x_fp32 * rstd).to(bf16) * weight
-        const float lo = bf16_round(bf16lo(ws[j]) * rstd) * wf[2 * j];
-        const float hi = bf16_round(bf16hi(ws[j]) * rstd) * wf[2 * j + 1];
-        o[j] = pack_bf16x2(lo, hi);
+        // reference: (x_fp32 * rstd).to(bf16) * weight   -> one packed convert, one packed bf16 multiply (the product of
+        // two bf16 values is exact in fp32, so mul.rn.bf16x2 rounds once, like the fp32 product rounded to bf16)
+        const uint32_t t = pack_bf16x2(bf16lo(ws[j]) * rstd, bf16hi(ws[j]) * rstd);
+        o[j] = mul_bf16x2(t, wq[j]);
       }
-      Y[row * nvec + c] = make_uint4(o[0], o[1], o[2], o[3]);
+      if (c < nvec) Y[row * nvec + c] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -90,7 +117,8 @@ __global__ void __launch_bounds__(256, (NV <= 16) ? 2 : 1) rmsnorm_fwd_kernel(co
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kNormBwdPartials = 592;  // 4 CTAs per SM x 148
 
-__global__ void __launch_bounds__(1024) rmsnorm_bwd_kernel(const uint4* __restrict__ S, const uint4* __restrict__ dY,
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) rmsnorm_bwd_kernel(const uint4* __restrict__ S, const uint4* __restrict__ dY,
                                                            const uint4* __restrict__ dS_extra,
                                                            const void* __restrict__ w, int w_is_f32,
                                                            const float* __restrict__ rstd_in, uint4* __restrict__ dS,
@@ -114,14 +142,35 @@ __global__ void __launch_bounds__(1024) rmsnorm_bwd_kernel(const uint4* __restri
     }
   }
   float dw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // the next row's operands are requested before the current row's block reduction, so HBM latency hides behind it
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  uint4 sv = zero4, gv = zero4, ev = zero4;
+  float rstd = 0.f;
+  int64_t row = blockIdx.x;
+  if (row < rows) {
+    rstd = rstd_in[row];
+    if (active) {
+      sv = S[row * nvec + t];
+      gv = dY[row * nvec + t];
+      if (dS_extra) ev = dS_extra[row * nvec + t];
+    }
+  }
   int it = 0;
-  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+  for (; row < rows; row += gridDim.x, ++it) {
+    const int64_t nrow = row + gridDim.x;
+    uint4 sv_n = zero4, gv_n = zero4, ev_n = zero4;
+    float rstd_n = 0.f;
+    if (nrow < rows) {
+      rstd_n = rstd_in[nrow];
+      if (active) {
+        sv_n = S[nrow * nvec + t];
+        gv_n = dY[nrow * nvec + t];
+        if (dS_extra) ev_n = dS_extra[nrow * nvec + t];
+      }
+    }
     float xn[8], g[8];
     float dot = 0.f;
-    const float rstd = rstd_in[row];
     if (active) {
-      const uint4 sv = S[row * nvec + t];
-      const uint4 gv = dY[row * nvec + t];
       const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
       const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
@@ -129,8 +178,9 @@ __global__ void __launch_bounds__(1024) rmsnorm_bwd_kernel(const uint4* __restri
         xn[2 * j] = bf16lo(sw[j]) * rstd;
         xn[2 * j + 1] = bf16hi(sw[j]) * rstd;
         const float g0 = bf16lo(gw[j]), g1 = bf16hi(gw[j]);
-        dw[2 * j] += g0 * bf16_round(xn[2 * j]);
-        dw[2 * j + 1] += g1 * bf16_round(xn[2 * j + 1]);
+        const uint32_t xr = pack_bf16x2(xn[2 * j], xn[2 * j + 1]);     // the bf16 normalised activations of the forward
+        dw[2 * j] += g0 * bf16lo(xr);
+        dw[2 * j + 1] += g1 * bf16hi(xr);
         g[2 * j] = g0 * wf[2 * j];
         g[2 * j + 1] = g1 * wf[2 * j + 1];
         dot += g[2 * j] * xn[2 * j] + g[2 * j + 1] * xn[2 * j + 1];
@@ -145,26 +195,41 @@ __global__ void __launch_bounds__(1024) rmsnorm_bwd_kernel(const uint4* __restri
     const float mean_dot = tot / float(d);
     if (active) {
       uint32_t o[4];
-      uint4 ev = make_uint4(0, 0, 0, 0);
-      if (dS_extra) ev = dS_extra[row * nvec + t];
       const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float lo = rstd * (g[2 * j] - xn[2 * j] * mean_dot);
-        float hi = rstd * (g[2 * j + 1] - xn[2 * j + 1] * mean_dot);
-        if (dS_extra) {
-          lo = bf16_round(lo) + bf16lo(ew[j]);
-          hi = bf16_round(hi) + bf16hi(ew[j]);
-        }
+        const float lo = rstd * (g[2 * j] - xn[2 * j] * mean_dot);
+        const float hi = rstd * (g[2 * j + 1] - xn[2 * j + 1] * mean_dot);
         o[j] = pack_bf16x2(lo, hi);
+        if (dS_extra) o[j] = add_bf16x2(o[j], ew[j]);      // bf16 + bf16 of the residual branch, rounded once
       }
       dS[row * nvec + t] = make_uint4(o[0], o[1], o[2], o[3]);
     }
+    sv = sv_n; gv = gv_n; ev = ev_n; rstd = rstd_n;
   }
   if (active) {
     float4* out = reinterpret_cast<float4*>(dW_partial + int64_t(blockIdx.x) * d + 8 * t);
     out[0] = make_float4(dw[0], dw[1], dw[2], dw[3]);
     out[1] = make_float4(dw[4], dw[5], dw[6], dw[7]);
+  }
+}
+
+// column sums of the [n_part, d] partials in a fixed order (deterministic): 32 columns per CTA, 32 row lanes
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ part, int n_part, int d,
+                                                      float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  float acc = 0.f;
+  if (col < d)
+    for (int r = ry; r < n_part; r += 32) acc += part[int64_t(r) * d + col];
+  tile[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && col < d) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) s += tile[r][cx];
+    out[col] = s;
   }
 }
 
@@ -334,9 +399,15 @@ extern "C" int tn_rmsnorm_fwd_bf16(const void* X, const void* R, const void* w, 
   const int nv = (nvec + 31) / 32;
   const unsigned grid = unsigned((rows + 7) / 8);
 #define TN_LAUNCH_NORM(NV)                                                                                         \
-  rmsnorm_fwd_kernel<NV><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(X), static_cast<const uint4*>(R), w,  \
-                                                   w_is_f32, static_cast<uint4*>(S_out), static_cast<uint4*>(Y),   \
-                                                   rstd, rows, d, eps)
+  do {                                                                                                             \
+    if (R)                                                                                                         \
+      rmsnorm_fwd_kernel<NV, true><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(X),                         \
+          static_cast<const uint4*>(R), w, w_is_f32, static_cast<uint4*>(S_out), static_cast<uint4*>(Y), rstd,    \
+          rows, d, eps);                                                                                           \
+    else                                                                                                           \
+      rmsnorm_fwd_kernel<NV, false><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(X), nullptr, w, w_is_f32, \
+          nullptr, static_cast<uint4*>(Y), rstd, rows, d, eps);                                                    \
+  } while (0)
   if (nv <= 1) TN_LAUNCH_NORM(1);
   else if (nv <= 2) TN_LAUNCH_NORM(2);
   else if (nv <= 4) TN_LAUNCH_NORM(4);
@@ -349,18 +420,27 @@ extern "C" int tn_rmsnorm_fwd_bf16(const void* X, const void* R, const void* w, 
 }
 
 extern "C" int tn_rmsnorm_bwd_bf16(const void* S, const void* dY, const void* dS_extra, const void* w, int w_is_f32,
-                                   const float* rstd, void* dS, float* dW_partial, int num_partials, int64_t rows,
-                                   int d, tn_stream_t stream_) {
+                                   const float* rstd, void* dS, float* dW_partial, int num_partials, float* dW,
+                                   int64_t rows, int d, tn_stream_t stream_) {
   clear_error();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TN_REQUIRE(S && dY && w && rstd && dS && dW_partial, "tn_rmsnorm_bwd_bf16: null pointer");
   TN_REQUIRE(d > 0 && d % 8 == 0 && d <= 8192, "tn_rmsnorm_bwd_bf16: d=%d must be a multiple of 8 and <= 8192", d);
   TN_REQUIRE(num_partials == kNormBwdPartials, "tn_rmsnorm_bwd_bf16: dW_partial must have %d rows", kNormBwdPartials);
   const int threads = ((d / 8 + 31) / 32) * 32;
-  rmsnorm_bwd_kernel<<<kNormBwdPartials, threads, 0, stream>>>(
-      static_cast<const uint4*>(S), static_cast<const uint4*>(dY), static_cast<const uint4*>(dS_extra), w, w_is_f32, rstd,
-      static_cast<uint4*>(dS), dW_partial, rows, d);
+  if (threads <= 512)
+    rmsnorm_bwd_kernel<512><<<kNormBwdPartials, threads, 0, stream>>>(
+        static_cast<const uint4*>(S), static_cast<const uint4*>(dY), static_cast<const uint4*>(dS_extra), w, w_is_f32,
+        rstd, static_cast<uint4*>(dS), dW_partial, rows, d);
+  else
+    rmsnorm_bwd_kernel<1024><<<kNormBwdPartials, threads, 0, stream>>>(
+        static_cast<const uint4*>(S), static_cast<const uint4*>(dY), static_cast<const uint4*>(dS_extra), w, w_is_f32,
+        rstd, static_cast<uint4*>(dS), dW_partial, rows, d);
   TN_CHECK_CUDA(cudaGetLastError());
+  if (dW) {   // final weight gradient: column sums over the partial rows that were written (CTAs beyond `rows` wrote zeros)
+    colsum_kernel<<<unsigned((d + 31) / 32), 1024, 0, stream>>>(dW_partial, kNormBwdPartials, d, dW);
+    TN_CHECK_CUDA(cudaGetLastError());
+  }
   return TN_OK;
 }
 

@@ -271,12 +271,12 @@ def rmsnorm_bwd(s: torch.Tensor, dy: torch.Tensor, w: torch.Tensor, rstd: torch.
     rows, d = s.shape
     ds = torch.empty_like(s)
     part = torch.empty((_norm_partials, d), dtype=torch.float32, device=s.device)
+    dw = torch.empty(d, dtype=torch.float32, device=s.device)
     w = w.detach()
     _lib.call("tn_rmsnorm_bwd_bf16", s.data_ptr(), dy.data_ptr(), None if ds_extra is None else ds_extra.data_ptr(),
               w.data_ptr(), int(w.dtype == torch.float32), rstd.data_ptr(), ds.data_ptr(), part.data_ptr(),
-              _norm_partials, rows, d, _st())
-    n_used = min(rows, _norm_partials)
-    return ds, part[:n_used].sum(0)
+              _norm_partials, dw.data_ptr(), rows, d, _st())
+    return ds, dw
 
 
 def rope_table(position_ids: torch.Tensor, inv_freq: torch.Tensor, scaling: float = 1.0):

@@ -186,3 +186,54 @@ def test_matches_hf_flex_attention_path():
     # (HF recomputes the rope frequencies in fp32 even when the module was cast to bf16; ours does the same)
     logits = ours(input_ids=ids, attention_mask=doc, position_ids=pos).logits
     _check_logits(logits, ref, doc > 0)
+
+
+def test_stock_hf_llama_with_b200_kernels_patched_in():
+    """The inner seam: stock HF LlamaForCausalLM whose RMSNorm / MLP / RoPE / attention arithmetic is
+    swapped Liger-style for the B200 kernels == the same HF model run eagerly with the dense document mask,
+    forward and parameter gradients (both bf16 models, so tolerances are bf16-vs-bf16)."""
+    dev = require_cuda()
+    import importlib
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from transformers.models.llama import modeling_llama
+    from touchnet_b200 import train_spec
+    hf_cfg = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                         num_key_value_heads=1, head_dim=128, vocab_size=512, rms_norm_eps=1e-5, rope_theta=500000.0,
+                         rope_scaling=dict(LLAMA3), tie_word_embeddings=False, attention_bias=False)
+    hf_cfg._attn_implementation = "eager"
+    torch.manual_seed(5)
+    hf = LlamaForCausalLM(hf_cfg)
+    with torch.no_grad():
+        for p_ in hf.parameters():
+            if p_.dim() == 2:
+                p_.normal_(0, 0.05)
+    hf = hf.to(dev).to(torch.bfloat16)
+    B, T = 2, 256
+    doc, pos = packed_doc_ids(B, T, [[100, 120], [256]], dev)
+    ids = torch.randint(0, 512, (B, T), device=dev)
+    allow = mo.doc_causal_allow(doc)[:, None]                          # [B,1,T,T] bool
+    mask4 = torch.zeros(allow.shape, dtype=torch.bfloat16, device=dev).masked_fill(~allow, float("-inf"))
+    mask4[(doc == 0)[:, None, :, None].expand_as(mask4)] = 0.0         # keep padding rows finite in eager softmax
+    tgt = torch.randn(B, T, 512, device=dev)
+    valid = doc > 0
+
+    def run(**kw):
+        hf.zero_grad()
+        lg = hf(input_ids=ids, position_ids=pos, **kw).logits
+        ((lg.float() * tgt)[valid]).mean().backward()
+        return lg.detach(), {n: p.grad.detach().clone() for n, p in hf.named_parameters()}
+
+    ref, ref_g = run(attention_mask=mask4)
+    saved = (modeling_llama.apply_rotary_pos_emb, modeling_llama.LlamaRMSNorm.forward, modeling_llama.LlamaMLP.forward)
+    try:
+        train_spec.apply_b200_kernels_to_hf_llama()
+        hf.config._attn_implementation = "touchnet_b200"
+        with train_spec.packed_document_ids(doc):
+            ours, ours_g = run(attention_mask=None)
+    finally:
+        (modeling_llama.apply_rotary_pos_emb, modeling_llama.LlamaRMSNorm.forward, modeling_llama.LlamaMLP.forward) = saved
+        hf.config._attn_implementation = "eager"
+    _check_logits(ours, ref, valid)
+    for n in ref_g:
+        e = rel_err(ours_g[n].float(), ref_g[n].float())
+        assert e < 4e-2, (n, e)

@@ -157,4 +157,81 @@ def register_hf_attention(name: str = "touchnet_b200") -> bool:
         ALL_ATTENTION_FUNCTIONS.register(name, hf_attention_forward)
     except AttributeError:
         ALL_ATTENTION_FUNCTIONS[name] = hf_attention_forward
+    try:    # transformers >= 4.53 builds masks through a second registry; ours needs none (document ids drive the kernel)
+        from transformers.masking_utils import ALL_MASK_ATTENTION_FUNCTIONS
+        ALL_MASK_ATTENTION_FUNCTIONS.register(name, _no_mask)
+    except Exception:
+        pass
     return True
+
+
+def _no_mask(*args, **kwargs):
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Liger-style patching of the stock HF Llama modules (SURVEY 8(b) "inner operator API")
+# ---------------------------------------------------------------------------------------------------------------
+class _HFRopeFn(torch.autograd.Function):
+    """`apply_rotary_pos_emb(q [B,H,T,hd], k [B,KV,T,hd], cos [B,T,hd], sin)` (hf: modeling_llama.py:151-168) on the
+    projection outputs as they lie in memory ([B,T,H,hd] behind the transpose), one kernel per tensor."""
+
+    @staticmethod
+    def forward(ctx, q, k, cos, sin):
+        B, H, T, hd = q.shape
+        KV = k.shape[1]
+        half = hd // 2
+        ct = cos[..., :half].reshape(B * T, half).to(torch.bfloat16).contiguous()
+        st = sin[..., :half].reshape(B * T, half).to(torch.bfloat16).contiguous()
+        q2 = q.transpose(1, 2).reshape(B * T, H * hd).to(torch.bfloat16, copy=True)
+        k2 = k.transpose(1, 2).reshape(B * T, KV * hd).to(torch.bfloat16, copy=True)
+        ops.rope_apply_(q2, ct, st, H, hd)
+        ops.rope_apply_(k2, ct, st, KV, hd)
+        ctx.save_for_backward(ct, st)
+        ctx.dims = (B, T, H, KV, hd, q.dtype)
+        return q2.view(B, T, H, hd).transpose(1, 2).to(q.dtype), k2.view(B, T, KV, hd).transpose(1, 2).to(k.dtype)
+
+    @staticmethod
+    def backward(ctx, dq, dk):
+        ct, st = ctx.saved_tensors
+        B, T, H, KV, hd, dt = ctx.dims
+        dq2 = dq.transpose(1, 2).reshape(B * T, H * hd).to(torch.bfloat16, copy=True)
+        dk2 = dk.transpose(1, 2).reshape(B * T, KV * hd).to(torch.bfloat16, copy=True)
+        ops.rope_apply_(dq2, ct, st, H, hd, inverse=True)
+        ops.rope_apply_(dk2, ct, st, KV, hd, inverse=True)
+        return dq2.view(B, T, H, hd).transpose(1, 2).to(dt), dk2.view(B, T, KV, hd).transpose(1, 2).to(dt), None, None
+
+
+def _hf_apply_rotary_pos_emb(q, k, cos, sin, position_ids=None, unsqueeze_dim=1):
+    return _HFRopeFn.apply(q, k, cos, sin)
+
+
+def _hf_rmsnorm_forward(self, hidden_states):
+    return ops.rms_norm(hidden_states, self.weight, self.variance_epsilon)
+
+
+def _hf_mlp_forward(self, x):
+    if self.gate_proj.bias is not None or getattr(self.config, "hidden_act", "silu") != "silu":
+        raise ops._lib.TouchNetB200Error("touchnet_b200 MLP kernel: SwiGLU (silu) without biases only")
+    x2 = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+    h = ops.swiglu_mlp_in(x2, self.gate_proj.weight, self.up_proj.weight)
+    return ops.linear(h, self.down_proj.weight).to(x.dtype)
+
+
+def apply_b200_kernels_to_hf_llama(rope: bool = True, rms_norm: bool = True, swiglu: bool = True,
+                                   attention: bool = True) -> None:
+    """Swap the arithmetic of the STOCK transformers Llama modules for the B200 kernels, the way the reference lets
+    Liger do it (`apply_liger_kernel_to_llama` in `additional_pre_init_fn`, ref: touchnet/models/llama/__init__.py:11-15):
+    `LlamaRMSNorm.forward`, `LlamaMLP.forward`, `apply_rotary_pos_emb` are replaced in `transformers.models.llama.
+    modeling_llama`, and "touchnet_b200" is registered as an attention implementation (select it with
+    `config._attn_implementation = "touchnet_b200"` and wrap the call in `packed_document_ids(doc_ids)`).
+    Module structure, parameters and state-dict keys stay HF's; head_dim must be 128 for the attention kernel."""
+    from transformers.models.llama import modeling_llama
+    if rope:
+        modeling_llama.apply_rotary_pos_emb = _hf_apply_rotary_pos_emb
+    if rms_norm:
+        modeling_llama.LlamaRMSNorm.forward = _hf_rmsnorm_forward
+    if swiglu:
+        modeling_llama.LlamaMLP.forward = _hf_mlp_forward
+    if attention:
+        register_hf_attention()

@@ -207,6 +207,19 @@ int tn_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float lr, float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
                  float bias_correction2_sqrt, const float* grad_scale, tn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Device-side assembly of the integer side of a packed batch: the per-document slice assignments of
+ * touchnet/models/llama/processing_llama.py:64-102 and touchnet/models/touch_audio/processing_touch_audio.py:176-206.
+ * The host keeps the greedy placement (row / offset / document id per document) and ships the concatenated text tokens;
+ * the five [B,T] int64 buffers are filled here: defaults pad / -100 / 0 / 0 / 1, then per document
+ *   position_ids = 0..total-1, attention_mask = sid, sentence_lens = n_txt over its `audio + n_txt` positions,
+ *   input_ids = [bos, tokens...], labels = [tokens..., eos] over the text positions (n_txt = n_tokens + 1).
+ */
+int tn_pack_layout_i64(const int32_t* doc_row, const int32_t* doc_off, const int32_t* doc_audio, const int32_t* doc_sid,
+                       const int64_t* tok_off, const int64_t* tokens, int n_docs, int B, int T, int64_t pad, int64_t bos,
+                       int64_t eos, int64_t* input_ids, int64_t* labels, int64_t* position_ids, int64_t* attention_mask,
+                       int64_t* sentence_lens, tn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,3 +66,26 @@ def test_synthetic_batches_have_reference_layout():
         seg = buf["attention_mask"][u["row"], u["offset"]:u["offset"] + u["frames"]]
         assert (seg == seg[0]).all() and seg[0] > 0
         assert (buf["labels"][u["row"], u["offset"]:u["offset"] + u["frames"]] == -100).all()   # no labels on audio
+
+
+def test_plan_documents_reproduces_the_greedy_placement():
+    """Host side of the device assembly: the compact per-document table places every document
+    exactly where batch_pairaudio_pairtext_packed / batch_text put it (buffers rebuilt from the table with numpy)."""
+    import numpy as np
+    from touchnet_b200 import batching
+    B, T = 2, 1024
+    host, placed = batching.plan_audio_text_batch(11, B, T, 1000, stride=4, max_s=6.0)
+    plan = batching.plan_documents(batching.synthetic_utterances(11, 1000, stride=4, max_s=6.0), B, T, with_audio=True)
+    tok = batching.SYN_TOKENIZER
+    ids = np.full((B, T), tok.pad, np.int64); lab = np.full((B, T), -100, np.int64)
+    pos = np.zeros((B, T), np.int64); doc = np.zeros((B, T), np.int64); sl = np.ones((B, T), np.int64)
+    toks = plan["tokens"].numpy()
+    for i in range(len(plan["doc_row"])):
+        b, t, a, sid = (int(plan[k][i]) for k in ("doc_row", "doc_off", "doc_audio", "doc_sid"))
+        tk = toks[int(plan["tok_off"][i]):int(plan["tok_off"][i + 1])]
+        n = len(tk) + 1
+        ids[b, t + a:t + a + n] = [tok.bos] + list(tk); lab[b, t + a:t + a + n] = list(tk) + [tok.eos]
+        pos[b, t:t + a + n] = np.arange(a + n); doc[b, t:t + a + n] = sid; sl[b, t:t + a + n] = n
+    for k, v in (("input_ids", ids), ("labels", lab), ("position_ids", pos), ("attention_mask", doc), ("sentence_lens", sl)):
+        assert np.array_equal(host[k].numpy(), v), k
+    assert plan["num_sentence"] == host["num_sentence"] == len(placed)

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "tn_bestrq_tokenize_f32": [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp, _vp],
     "tn_pack_ce_fwd_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _vp],
     "tn_pack_ce_bwd_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _f, _i64, _i, _vp],
+    "tn_pack_layout_i64": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "tn_sumsq_num_partials": [],
     "tn_sumsq_f32": [_vp, _i64, _vp, _vp, _vp],
     "tn_scale_f32": [_vp, _i64, _vp, _vp],
@@ -84,7 +85,8 @@ def load(path: str | None = None) -> ctypes.CDLL:
 
 
 # kernels launched per entry point (for bench.py's `gpu_launches` claim)
-_LAUNCHES = {"tn_attn_prep": 2, "tn_attn_bwd_bf16": 3, "tn_logmel_power_f32": 2, "tn_rmsnorm_bwd_bf16": 2}
+_LAUNCHES = {"tn_attn_prep": 2, "tn_attn_bwd_bf16": 3, "tn_logmel_power_f32": 2, "tn_rmsnorm_bwd_bf16": 2,
+             "tn_pack_layout_i64": 2}
 launch_count = 0
 _hooks = []   # callables(name, phase) with phase in {"pre", "post"}; bench.py uses them to time kernel classes
 

@@ -180,3 +180,58 @@ def plan_audio_text_batch(seed: int, B: int, T: int, vocab: int, stride: int = 4
         sid += 1
     buf["shift_labels"] = buf["labels"]
     return buf, placed
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device-side assembly of the integer buffers
+# ---------------------------------------------------------------------------------------------------------------
+def plan_documents(samples: Iterable[dict], B: int, T: int, with_audio: bool) -> dict:
+    """The greedy first-fit-in-order placement of `batch_text` / `batch_pairaudio_pairtext_packed` for ONE batch, as compact
+    per-document tables (host side, integers only): row, offset, audio positions, document id, token offsets + tokens.
+    Consumes `samples` until the batch is full (the sample that does not fit is dropped, like the synthetic planner)."""
+    rows, offs, auds, sids, tok_off, toks = [], [], [], [], [0], []
+    b = t = 0
+    sid = 1
+    for s in samples:
+        a = int(s["num_feat_frames"] if "num_feat_frames" in s else (s["audiofeat"].size(0) if with_audio else 0)) if with_audio else 0
+        n_txt = len(s["input_ids"]) + 1
+        total = a + n_txt
+        if total > T:
+            continue
+        if t + total > T:
+            if b == B - 1:
+                break
+            b += 1
+            t = 0
+            sid = 1
+        rows.append(b); offs.append(t); auds.append(a); sids.append(sid)
+        toks.extend(int(x) for x in s["input_ids"])
+        tok_off.append(len(toks))
+        t += total
+        sid += 1
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32)
+    return {"doc_row": i32(rows), "doc_off": i32(offs), "doc_audio": i32(auds), "doc_sid": i32(sids),
+            "tok_off": torch.tensor(tok_off, dtype=torch.int64), "tokens": torch.tensor(toks or [0], dtype=torch.int64),
+            "num_sentence": len(rows), "B": B, "T": T}
+
+
+def assemble_on_device(plan: dict, device, tokenizer=SYN_TOKENIZER) -> dict:
+    """Fill input_ids / labels / position_ids / attention_mask / sentence_lens [B,T] int64 ON THE GPU from a
+    `plan_documents` table (H2D: the tokens + 5 small vectors instead of five [B,T] buffers).  Same keys as the host
+    batchers' buffers (ref: processing_llama.py:24-104, processing_touch_audio.py:117-214)."""
+    from . import _lib, ops
+    B, T = plan["B"], plan["T"]
+    dev = torch.device(device)
+    d = {k: plan[k].to(dev, non_blocking=True) for k in ("doc_row", "doc_off", "doc_audio", "doc_sid", "tok_off", "tokens")}
+    out = {k: torch.empty((B, T), dtype=torch.int64, device=dev)
+           for k in ("input_ids", "labels", "position_ids", "attention_mask", "sentence_lens")}
+    ops._chk(out["input_ids"], "output buffers")
+    n_docs = int(plan["doc_row"].numel())
+    _lib.call("tn_pack_layout_i64", d["doc_row"].data_ptr(), d["doc_off"].data_ptr(), d["doc_audio"].data_ptr(),
+              d["doc_sid"].data_ptr(), d["tok_off"].data_ptr(), d["tokens"].data_ptr() if n_docs else None, n_docs, B, T,
+              int(tokenizer.pad), int(tokenizer.bos), int(tokenizer.eos), out["input_ids"].data_ptr(),
+              out["labels"].data_ptr(), out["position_ids"].data_ptr(), out["attention_mask"].data_ptr(),
+              out["sentence_lens"].data_ptr(), ops._st())
+    out["num_sentence"] = plan["num_sentence"]
+    out["shift_labels"] = out["labels"]
+    return out

@@ -34,6 +34,9 @@ int tn_device_check(void);
  * neighbouring layers need SMs of their own to overlap with them.  Leave `sms` SMs unused by persistent grids
  * (0 = default, single GPU).  Process-wide. */
 int tn_set_sm_margin(int sms);
+/* Tuning knob: raster group of the CTA-pair GEMM = number of 256-row M blocks whose tiles are walked across all N blocks
+ * before moving on (default 8; decides which operand strips stay L2-resident between waves).  Results do not depend on it. */
+int tn_set_gemm_group(int m_blocks);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GEMM  D[M,N] = A·Bᵀ (+ R)          tcgen05 / TMEM / TMA, bf16 in, fp32 accumulate.

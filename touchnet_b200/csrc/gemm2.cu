@@ -16,7 +16,6 @@ constexpr int P_BM = 128;        // rows of A (and of D) per CTA
 constexpr int P_BN = 256;        // D columns per cluster tile; each CTA stages P_BN/2 rows of B
 constexpr int P_BK = 64;
 constexpr int P_THREADS = 256;
-constexpr int P_GROUP = 8;
 constexpr int P_A_BYTES = P_BM * P_BK * 2;        // 16 KB
 constexpr int P_B_BYTES = (P_BN / 2) * P_BK * 2;  // 16 KB
 constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
@@ -34,6 +33,7 @@ struct PairCfg {
 struct PairParams {
   int M, N, K;
   int num_m, num_n, num_k;   // num_m in units of 256 rows
+  int group;                 // raster: tiles walk `group` M blocks x all N blocks before moving down (L2 reuse of A)
   const void* R;
   int64_t ldr;
   // segmented operands: several weight tensors that are separate nn.Parameters (q/k/v projections) behave as one GEMM
@@ -50,11 +50,11 @@ struct PairParams {
   int rope_end;
 };
 
-__device__ __forceinline__ void pair_decode_tile(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
-  const int per_group = P_GROUP * num_n;
+__device__ __forceinline__ void pair_decode_tile(int tile, int num_m, int num_n, int group, int& m_blk, int& n_blk) {
+  const int per_group = group * num_n;
   const int g = tile / per_group;
-  const int first_m = g * P_GROUP;
-  const int gsize = min(num_m - first_m, P_GROUP);
+  const int first_m = g * group;
+  const int gsize = min(num_m - first_m, group);
   const int r = tile - g * per_group;
   m_blk = first_m + (r % gsize);
   n_blk = r / gsize;
@@ -114,7 +114,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int m_blk, n_blk;
-        pair_decode_tile(tile, p.num_m, p.num_n, m_blk, n_blk);
+        pair_decode_tile(tile, p.num_m, p.num_n, p.group, m_blk, n_blk);
         const int m0 = m_blk * 256 + int(rank) * P_BM;
         int n0 = (EPI == 1) ? n_blk * 128 : n_blk * P_BN + int(rank) * (P_BN / 2);
         const CUtensorMap* bmap = &tmB;
@@ -197,7 +197,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t n_issued = 0;                       // staging rounds issued so far (buffer ring position)
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int m_blk, n_blk;
-      pair_decode_tile(tile, p.num_m, p.num_n, m_blk, n_blk);
+      pair_decode_tile(tile, p.num_m, p.num_n, p.group, m_blk, n_blk);
       const int row0 = m_blk * 256 + int(rank) * P_BM;
       const int row = row0 + int(r);
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -432,6 +432,7 @@ int gemm_pair_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int6
   PairParams p{};
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
+  p.group = gemm_group();
   p.R = R; p.ldr = ldr;
   CUtensorMap tmA, tmB, tmD;
   int rc;
@@ -466,6 +467,7 @@ int gemm_pair_seg_dispatch(int mode, const void* A, int64_t lda, const void* con
   }
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
+  p.group = gemm_group();
   p.off1 = seg[0]; p.off2 = seg[0] + seg[1];
   CUtensorMap tmA, tmB[3], tmD[3];
   int rc;
@@ -502,6 +504,7 @@ int gemm_pair_swiglu_dispatch(const void* X, int64_t ldx, const void* Wg, const 
   PairParams p{};
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + 127) / 128; p.num_k = (K + P_BK - 1) / P_BK;
+  p.group = gemm_group();
   CUtensorMap tmA, tmG, tmU, tmDG, tmDU, tmDH;
   int rc;
   if ((rc = encode_tmap_2d(&tmA, X, 2, uint64_t(K), uint64_t(M), uint64_t(ldx) * 2, 64, P_BM, true))) return rc;

@@ -87,6 +87,9 @@ int encode_tmap_3d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t d
 }
 
 static int g_sm_margin = 0;
+static int g_gemm_group = 8;
+
+int gemm_group() { return g_gemm_group; }
 
 int sm_count() {
   static int n = 0;
@@ -110,6 +113,12 @@ int tn_version(void) { return TOUCHNET_B200_VERSION; }
 int tn_set_sm_margin(int sms) {
   if (sms < 0 || sms > 120) return tn::fail(tn::TN_ERR_ARG, "tn_set_sm_margin: %d out of range [0,120]", sms);
   tn::g_sm_margin = sms;
+  return tn::TN_OK;
+}
+
+int tn_set_gemm_group(int m_blocks) {
+  if (m_blocks < 1 || m_blocks > 64) return tn::fail(tn::TN_ERR_ARG, "tn_set_gemm_group: %d out of range [1,64]", m_blocks);
+  tn::g_gemm_group = m_blocks;
   return tn::TN_OK;
 }
 

@@ -35,5 +35,6 @@ int encode_tmap_3d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t d
                    bool swizzle128);
 
 int sm_count();
+int gemm_group();   // raster group of the CTA-pair GEMM (tn_set_gemm_group)
 
 }  // namespace tn

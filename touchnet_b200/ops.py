@@ -9,7 +9,6 @@ from __future__ import annotations
 
 import math
 import os
-import sys
 from typing import Optional
 
 import torch
@@ -152,63 +151,6 @@ def prefetch_bf16_weights(module: torch.nn.Module) -> int:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# raster autotuning of the CTA-pair GEMM
-# ---------------------------------------------------------------------------------------------------------------
-# The persistent GEMM walks its 256x256 output tiles in groups of `g` M-blocks x all N-blocks (tn_set_gemm_group).  Which
-# operand strips stay L2-resident between waves - and with it DRAM traffic, and on a power-capped part the clock - depends
-# on g, the shape and the operand majorness: measured spread on the Llama-3-8B shapes is up to 1.39x (dgrad of down_proj:
-# g=8 978 TFLOP/s, g=32 1363; tools/time_gemm_group.py).  There is no single good value, so the first launch of every
-# distinct (entry point, layout, M, N, K) times the candidates on its own operands and the winner is cached for the
-# process.  Results do not depend on the raster (k-order inside a tile is fixed).  TN_GEMM_AUTOTUNE=0 pins g=8.
-_AUTOTUNE = os.environ.get("TN_GEMM_AUTOTUNE", "1") != "0"
-_GROUP_CANDIDATES = (1, 2, 4, 8, 16, 32, 64)
-_group_cache: dict = {}
-_cur_group = 8
-
-
-def _set_group(g: int) -> None:
-    global _cur_group
-    if g != _cur_group:
-        _lib.call("tn_set_gemm_group", g)
-        _lib.launch_count -= 1            # not a kernel launch
-        _cur_group = g
-
-
-def _with_tuned_group(key, M: int, N: int, launch) -> None:
-    """Run `launch()` (one idempotent GEMM launch on the current stream) under the best raster group for `key`."""
-    g = _group_cache.get(key)
-    if g is None:
-        g = 8
-        if _AUTOTUNE and M >= 256 and N >= 256 and M * N >= 256 * 256 * 64 and not torch.cuda.is_current_stream_capturing():
-            hooks, _lib._hooks = _lib._hooks, []          # tuning launches are not part of any measurement
-            count = _lib.launch_count
-            try:
-                best_t = None
-                for cand in _GROUP_CANDIDATES:
-                    if cand > 1 and cand // 2 >= (M + 255) // 256:
-                        break                              # the group already spans every M block
-                    _set_group(cand)
-                    launch()
-                    ts = []
-                    for _ in range(2):
-                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        e0.record(); launch(); e1.record()
-                        e1.synchronize()
-                        ts.append(e0.elapsed_time(e1))
-                    t = min(ts)
-                    if best_t is None or t < best_t * 0.985:   # prefer the smaller group unless clearly faster
-                        best_t, g = t, cand
-            finally:
-                _lib._hooks = hooks
-                _lib.launch_count = count
-            if os.environ.get("TN_GEMM_AUTOTUNE_LOG"):
-                print(f"[touchnet_b200] raster group {g:2d} for {key} ({best_t * 1e3:.0f} us)", file=sys.stderr, flush=True)
-        _group_cache[key] = g
-    _set_group(g)
-    launch()
-
-
-# ---------------------------------------------------------------------------------------------------------------
 # raw ops (no autograd)
 # ---------------------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out_f32: bool = False,
@@ -227,17 +169,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if residual is not None:
         assert residual.dtype == dt and residual.stride(-1) == 1
         residual = residual.reshape(M, N) if residual.dim() != 2 else residual
-    def launch(o=out):
-        _lib.call("tn_gemm_bf16", a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
-                  o.data_ptr(), o.stride(0), int(out_f32), None if residual is None else residual.data_ptr(),
-                  0 if residual is None else residual.stride(0), M, N, K, _st())
-
-    key = ("gemm", a_mn, b_mn, out_f32, residual is not None, M, N, K)
-    if key not in _group_cache and residual is not None and residual.data_ptr() == out.data_ptr():
-        scratch = torch.empty_like(out)          # in-place accumulate is not idempotent: tune into a scratch output
-        _with_tuned_group(key, M, N, lambda: launch(scratch))
-        del scratch
-    _with_tuned_group(key, M, N, launch)
+    _lib.call("tn_gemm_bf16", a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
+              out.data_ptr(), out.stride(0), int(out_f32), None if residual is None else residual.data_ptr(),
+              0 if residual is None else residual.stride(0), M, N, K, _st())
     return out
 
 
@@ -250,9 +184,8 @@ def gemm_swiglu(x: torch.Tensor, wg: torch.Tensor, wu: torch.Tensor, need_gu: bo
     h = torch.empty((M, N), dtype=BF16, device=x.device)
     g = torch.empty_like(h) if need_gu else None
     u = torch.empty_like(h) if need_gu else None
-    _with_tuned_group(("swiglu", need_gu, M, N, K), M, N, lambda: _lib.call(
-        "tn_gemm_swiglu_bf16", x.data_ptr(), x.stride(0), wg.data_ptr(), wu.data_ptr(), wg.stride(0),
-        None if g is None else g.data_ptr(), None if u is None else u.data_ptr(), h.data_ptr(), N, M, N, K, _st()))
+    _lib.call("tn_gemm_swiglu_bf16", x.data_ptr(), x.stride(0), wg.data_ptr(), wu.data_ptr(), wg.stride(0),
+              None if g is None else g.data_ptr(), None if u is None else u.data_ptr(), h.data_ptr(), N, M, N, K, _st())
     return g, u, h
 
 
@@ -270,10 +203,9 @@ def gemm_qkv_fwd(x, wq, wk, wv, rope=None):
     M, K = x.shape
     nq, nkv = wq.shape[0], wk.shape[0]
     out = torch.empty((M, nq + 2 * nkv), dtype=BF16, device=x.device)
-    _with_tuned_group(("qkv_fwd", rope is not None, M, nq, nkv, K), M, nq + 2 * nkv, lambda: _lib.call(
-        "tn_gemm_qkv_bf16", 0, x.data_ptr(), x.stride(0), wq.data_ptr(), wk.data_ptr(), wv.data_ptr(), wq.stride(0),
-        out.data_ptr(), None, None, out.stride(0), 0, nq, nkv, nkv, M, nq + 2 * nkv, K,
-        None if rope is None else rope[0].data_ptr(), None if rope is None else rope[1].data_ptr(), _st()))
+    _lib.call("tn_gemm_qkv_bf16", 0, x.data_ptr(), x.stride(0), wq.data_ptr(), wk.data_ptr(), wv.data_ptr(), wq.stride(0),
+              out.data_ptr(), None, None, out.stride(0), 0, nq, nkv, nkv, M, nq + 2 * nkv, K,
+              None if rope is None else rope[0].data_ptr(), None if rope is None else rope[1].data_ptr(), _st())
     return out
 
 
@@ -282,10 +214,9 @@ def gemm_qkv_dgrad(dqkv, wq, wk, wv):
     M, Kt = dqkv.shape
     d = wq.shape[1]
     out = torch.empty((M, d), dtype=BF16, device=dqkv.device)
-    _with_tuned_group(("qkv_dgrad", M, d, Kt), M, d, lambda: _lib.call(
-        "tn_gemm_qkv_bf16", 1, dqkv.data_ptr(), dqkv.stride(0), wq.data_ptr(), wk.data_ptr(), wv.data_ptr(),
-        wq.stride(0), out.data_ptr(), None, None, out.stride(0), 0, wq.shape[0], wk.shape[0], wv.shape[0], M, d, Kt,
-        None, None, _st()))
+    _lib.call("tn_gemm_qkv_bf16", 1, dqkv.data_ptr(), dqkv.stride(0), wq.data_ptr(), wk.data_ptr(), wv.data_ptr(),
+              wq.stride(0), out.data_ptr(), None, None, out.stride(0), 0, wq.shape[0], wk.shape[0], wv.shape[0], M, d, Kt,
+              None, None, _st())
     return out
 
 
@@ -299,10 +230,9 @@ def gemm_qkv_wgrad(dqkv, x, f32: bool, nq: int | None = None, nkv: int | None = 
     nkv = (Mt - nq) // 2 if nkv is None else nkv
     dt = torch.float32 if f32 else BF16
     outs = [torch.empty((n, d), dtype=dt, device=x.device) for n in (nq, nkv, nkv)]
-    _with_tuned_group(("qkv_wgrad", f32, Mt, d, Mred), Mt, d, lambda: _lib.call(
-        "tn_gemm_qkv_bf16", 2, dqkv.data_ptr(), dqkv.stride(0), x.data_ptr(), None, None, x.stride(0),
-        outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), d, int(f32), nq, nkv, nkv, Mt, d, Mred, None,
-        None, _st()))
+    _lib.call("tn_gemm_qkv_bf16", 2, dqkv.data_ptr(), dqkv.stride(0), x.data_ptr(), None, None, x.stride(0),
+              outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), d, int(f32), nq, nkv, nkv, Mt, d, Mred, None,
+              None, _st())
     return outs
 
 

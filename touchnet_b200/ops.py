@@ -506,7 +506,7 @@ def swiglu_mlp_in(x, wg, wu):
 
 class DecoderLayerFn(torch.autograd.Function):
     """One pre-norm decoder block as a single autograd node (hf: LlamaDecoderLayer.forward modeling_llama.py:303-333):
-    12 kernel launches forward, residual adds fused into the o_proj / down_proj GEMM epilogues, q/k/v projections one
+    7 kernel launches forward, residual adds fused into the o_proj / down_proj GEMM epilogues, q/k/v projections one
     segmented GEMM, the residual-branch gradient fused into the RMSNorm backward kernel.  Parameters stay separate
     nn.Linear weights (HF FQNs) so FSDP2 / DCP / convert_* of the reference keep working
     (ref: touchnet/models/helper_func.py:134-202).  Use `decoder_layer(...)`: it resolves the bf16 working copies of the

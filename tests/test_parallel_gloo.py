@@ -77,7 +77,40 @@ def _loss(logits, tgt, doc, denom):
     return ((logits.float() * tgt)[doc > 0]).sum() / denom
 
 
-def _tp_worker(rank, world, port, audio, bias, q):
+class FilePeerMemory:
+    """Test double of tensor_parallel.SymmPeerMemory: /dev/shm files mapped by every rank stand in for symmetric memory
+    (a store into views[peer] is visible to the peer after the barrier, like an NVLink P2P store)."""
+    _count = 0
+
+    def __init__(self, group, device):
+        self.group = group
+        self.size, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.paths = []
+
+    def alloc(self, shape, dtype):
+        FilePeerMemory._count += 1
+        numel = 1
+        for d in shape:
+            numel *= d
+        base = f"/dev/shm/tn_peer_{os.environ['MASTER_PORT']}_{FilePeerMemory._count}"
+        mine = f"{base}_{self.rank}"
+        torch.from_file(mine, shared=True, size=numel, dtype=dtype).zero_()          # creates the file
+        dist.barrier(self.group)
+        self.paths.append(mine)
+        return [torch.from_file(f"{base}_{r}", shared=True, size=numel, dtype=dtype).view(*shape) for r in range(self.size)]
+
+    def barrier(self):
+        dist.barrier(self.group)
+
+    def cleanup(self):
+        for p in self.paths:
+            try:
+                os.remove(p)
+            except OSError:
+                pass
+
+
+def _tp_worker(rank, world, port, audio, bias, q, peer=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -85,6 +118,9 @@ def _tp_worker(rank, world, port, audio, bias, q):
         cpu_ops_shim.install()
         from torch.distributed.device_mesh import init_device_mesh
         from touchnet_b200 import tensor_parallel
+        if peer:        # NCCL-free context: same code path as TN_TP_PEER=1 on GPUs, symmetric memory replaced by /dev/shm
+            os.environ["TN_TP_PEER"] = "1"
+            tensor_parallel.SymmPeerMemory = FilePeerMemory
         model, text = _build(audio, bias)
         B, T = 2, 256
         kw, doc, tgt = _inputs(B, T, text.vocab_size, audio)
@@ -113,9 +149,17 @@ def _tp_worker(rank, world, port, audio, bias, q):
             e = _rel(g.float(), ref_grads[n].float())
             if e > worst:
                 worst, worst_name = e, n
+        if peer:
+            ctx = (model.language_model.model if audio else model.model)._tn_tp_peer_ctx
+            assert isinstance(ctx, tensor_parallel.PeerTPContext) and len(ctx._kept) == 4      # h1, h2 of 2 blocks
+            ctx.mem.cleanup()
         q.put((rank, err_fwd, worst, worst_name))
     finally:
         dist.destroy_process_group()
+
+
+def _tp_worker_peer(rank, world, port, q):
+    _tp_worker(rank, world, port, True, True, q, peer=True)
 
 
 def _cp_worker(rank, world, port, q):
@@ -258,6 +302,15 @@ def _run(target, args, port_base, world=2):
 def test_tensor_parallel_matches_unsharded(audio, bias):
     for rank, err_fwd, worst, name in _run(_tp_worker, (audio, bias), 29700):
         assert err_fwd < 2e-2, (rank, err_fwd)       # bf16 rounding of partial sums before the reduce-scatter
+        assert worst < 3e-2, (rank, name, worst)
+
+
+def test_tensor_parallel_peer_memory_context_matches_unsharded():
+    """tensor_parallel.PeerTPContext (opt-in, TN_TP_PEER=1): the block's collectives as direct stores into the peers'
+    buffers - row-split GEMM launches whose outputs land in the destination rank's receive slot, gathers by peer stores,
+    one barrier each.  Symmetric memory is replaced by shared-memory files; B=2 exercises the per-batch-row indexing."""
+    for rank, err_fwd, worst, name in _run(_tp_worker_peer, (), 30340):
+        assert err_fwd < 2e-2, (rank, err_fwd)
         assert worst < 3e-2, (rank, name, worst)
 
 

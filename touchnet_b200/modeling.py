@@ -212,7 +212,8 @@ class B200LlamaModel(nn.Module):
             from . import tensor_parallel
             if attention_mask.shape[1] != T or position_ids.shape[1] != T:
                 raise TouchNetB200Error("tensor parallelism: attention_mask / position_ids must cover the whole sequence")
-            plan.tp = tensor_parallel.TPContext(tp_group, B)
+            plan.tp = tensor_parallel.make_context(tp_group, B, dev, cache_on=self)
+            plan.tp.begin_step()
         cos, sin = self.rotary_emb(position_ids)            # once per step
         x = inputs_embeds
         if x.dtype != torch.bfloat16:

@@ -522,7 +522,7 @@ class DecoderLayerFn(torch.autograd.Function):
             raise _lib.TouchNetB200Error("tensor parallelism and context parallelism cannot be combined in one block")
         h1, _, rstd1 = rmsnorm_fwd(x2, ln1, eps)
         if tp is not None:
-            h1 = tp.ag(h1)                                                   # [B*T, d]: every row, for the local heads
+            h1 = tp.gather_rows(h1, keep=True)                               # [B*T, d]: every row, for the local heads
         nq, nkv = wq.shape[0], wk.shape[0]
         rope_in_gemm = qkv_fusable(h1.shape[0], nq, nkv) and bq is None     # RoPE in the QKV GEMM epilogue
         if qkv_fusable(h1.shape[0], nq, nkv):
@@ -543,15 +543,15 @@ class DecoderLayerFn(torch.autograd.Function):
         if tp is None:
             x1 = gemm(o, wob, residual=x2)
         else:                                                                # partial sums over tp -> this rank's rows
-            x1 = tp.rs(gemm(o, wob)).add_(x2)
+            x1 = tp.gemm_reduce_scatter(o, wob, x2)
         h2, _, rstd2 = rmsnorm_fwd(x1, ln2, eps)
         if tp is not None:
-            h2 = tp.ag(h2)
+            h2 = tp.gather_rows(h2, keep=True)
         g, u, hm = gemm_swiglu(h2, wgb, wub)
         if tp is None:
             out = gemm(hm, wdb, residual=x1)
         else:
-            out = tp.rs(gemm(hm, wdb)).add_(x1)
+            out = tp.gemm_reduce_scatter(hm, wdb, x1)
         ctx.save_for_backward(x2, ln1, ln2, wqb, wkb, wvb, wob, wgb, wub, wdb, cos, sin, rstd1, h1, q, k, v, o, lse, x1,
                               rstd2, h2, g, u, hm)
         ctx.plan, ctx.H, ctx.KV, ctx.scale, ctx.has_bias = plan, H, KV, scale, bq is not None
@@ -569,7 +569,7 @@ class DecoderLayerFn(torch.autograd.Function):
         if d2.dtype != BF16:
             d2 = d2.to(BF16)
         # ---- MLP ----
-        d2f = d2 if tp is None else tp.ag(d2)          # backward of the forward reduce-scatter
+        d2f = d2 if tp is None else tp.gather_rows(d2)     # backward of the forward reduce-scatter
         dhm = gemm(d2f, wdb, b_mn=True)
         dwd = _wgrad(d2f, hm, f32)
         del d2f
@@ -581,10 +581,10 @@ class DecoderLayerFn(torch.autograd.Function):
         dwu = _wgrad(du, h2, f32)
         del dg, du
         if tp is not None:
-            dh2 = tp.rs(dh2)                           # backward of the forward all-gather
+            dh2 = tp.reduce_scatter(dh2)               # backward of the forward all-gather
         dx1, dln2 = rmsnorm_bwd(x1, dh2, ln2, rstd2, ds_extra=d2)
         # ---- attention ----
-        dx1f = dx1 if tp is None else tp.ag(dx1)
+        dx1f = dx1 if tp is None else tp.gather_rows(dx1)
         do = gemm(dx1f, wob, b_mn=True)
         dwo = _wgrad(dx1f, o, f32)
         del dx1f
@@ -616,7 +616,7 @@ class DecoderLayerFn(torch.autograd.Function):
         if ctx.has_bias:
             dbq = dq.float().sum(0).to(ctx.w_dtype); dbk = dk.float().sum(0).to(ctx.w_dtype); dbv = dv.float().sum(0).to(ctx.w_dtype)
         if tp is not None:
-            dh1 = tp.rs(dh1)
+            dh1 = tp.reduce_scatter(dh1)
         dx, dln1 = rmsnorm_bwd(x2, dh1, ln1, rstd1, ds_extra=dx1)
         if tp is not None:                             # replicated norm weights, sequence-sharded rows: sum the partials
             tp.all_reduce_(dln1)

@@ -82,6 +82,22 @@ class TPContext:
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
         return x
 
+    # -- what the decoder block calls (ops.DecoderLayerFn); PeerTPContext overrides these three --------------------
+    def begin_step(self) -> None:
+        """Called once per model forward, before the first block."""
+
+    def gather_rows(self, x: torch.Tensor, keep: bool = False) -> torch.Tensor:
+        """[B*Tl, C] -> [B*T, C].  keep=True: the result is saved for backward by the caller."""
+        return self.ag(x)
+
+    def reduce_scatter(self, partial: torch.Tensor) -> torch.Tensor:
+        """[B*T, C] partial sums -> [B*Tl, C] summed rows of this rank."""
+        return self.rs(partial)
+
+    def gemm_reduce_scatter(self, a: torch.Tensor, w: torch.Tensor, residual_s: torch.Tensor) -> torch.Tensor:
+        """reduce_scatter(a · wᵀ) + residual_s: the row-parallel projections (o_proj, down_proj) of the forward."""
+        return self.rs(ops.gemm(a, w)).add_(residual_s)
+
     def seq_slice(self, x: torch.Tensor) -> torch.Tensor:
         """This rank's rows of a full [B, T, ...] tensor."""
         Tl = x.shape[1] // self.size
@@ -226,3 +242,137 @@ def apply_tp(model: torch.nn.Module, tp_mesh) -> torch.nn.Module:
         if isinstance(mod, (modeling.B200LlamaModel, modeling.B200LlamaForCausalLM, modeling.B200TouchAudioForCausalLM)):
             mod.tp_group = tp_mesh.get_group()
     return model
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# NCCL-free variant: kernels store straight into the peers' memory (EXPERIMENTAL, opt-in with TN_TP_PEER=1)
+# ---------------------------------------------------------------------------------------------------------------
+class SymmPeerMemory:
+    """Symmetric buffers of one tp group through torch.distributed._symmetric_memory (CUDA IPC / NVLink P2P):
+    `alloc` returns, for every rank of the group, a tensor aliasing THAT rank's buffer, so a kernel whose output pointer
+    is `views[peer]` writes over NVLink into the peer's HBM."""
+
+    def __init__(self, group: dist.ProcessGroup, device: torch.device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._symm = symm_mem
+        self.group, self.device = group, device
+        self.size = dist.get_world_size(group)
+        self._handles = []
+
+    def alloc(self, shape, dtype) -> list:
+        t = self._symm.empty(*shape, dtype=dtype, device=self.device)
+        h = self._symm.rendezvous(t, self.group)
+        self._handles.append((t, h))
+        return [h.get_buffer(r, tuple(shape), dtype) for r in range(self.size)]
+
+    def barrier(self) -> None:
+        """Device-side barrier on the current stream: stores issued before it by any rank are visible to all after it."""
+        self._handles[0][1].barrier()
+
+
+class PeerTPContext(TPContext):
+    """The block's tp collectives without NCCL (SURVEY 8(e) B200 note: overlap / fusion over peer memory):
+
+      gemm_reduce_scatter   the row-parallel GEMM is launched once per destination rank on that rank's rows of A; its
+                            epilogue (TMA store) writes the partial tile directly into the destination's receive slot
+                            over NVLink while later tiles are still being multiplied - the transfer IS the epilogue.
+                            After one barrier every rank adds its tp receive slots (+ the residual, fused into the local
+                            launch).
+      gather_rows           each rank stores its rows into every rank's full buffer, one barrier.
+      reduce_scatter        (backward) peers' rows of the partial are copied into their receive slots, barrier, add.
+
+    Receive slots alternate between two buffers so that one barrier per collective suffices (a slot is rewritten only
+    after a later barrier, which its reader reaches after it has consumed the slot).  Buffers returned with keep=True are
+    per call site and live until the same call site of the next step (they are saved for backward), so activation
+    checkpointing is not supported with this context.
+
+    STATUS: written at the end of round 1 without GPU time left; the wiring is tested on CPU against the unsharded model
+    with shared-memory files standing in for symmetric memory (tests/test_parallel_gloo.py); it has NOT run on NVLink
+    hardware yet and is therefore opt-in (TN_TP_PEER=1)."""
+
+    def __init__(self, group: dist.ProcessGroup, B: int, mem):
+        super().__init__(group, B)
+        self.mem = mem
+        self._kept: dict = {}       # (call index, shape, dtype) -> views of the per-call-site gather buffers
+        self._pool: dict = {}       # (tag, shape, dtype) -> [views_parity0, views_parity1]
+        self._parity: dict = {}
+        self._calls = 0
+
+    def begin_step(self) -> None:
+        self._calls = 0
+
+    def _transient(self, tag, shape, dtype):
+        key = (tag, tuple(shape), dtype)
+        if key not in self._pool:
+            self._pool[key] = [self.mem.alloc(shape, dtype), self.mem.alloc(shape, dtype)]
+            self._parity[key] = 0
+        par = self._parity[key]
+        self._parity[key] = par ^ 1
+        return self._pool[key][par]
+
+    def _rows(self, full: torch.Tensor, r: int) -> torch.Tensor:
+        """Rank r's rows of a full [B*T, C] tensor as a [B, Tl, C] view."""
+        C = full.shape[-1]
+        return full.view(self.B, self.size, -1, C)[:, r]
+
+    def gather_rows(self, x: torch.Tensor, keep: bool = False) -> torch.Tensor:
+        rows, C = x.shape
+        shape = (rows * self.size, C)
+        if keep:
+            key = (self._calls, shape, x.dtype)
+            self._calls += 1
+            if key not in self._kept:
+                self._kept[key] = self.mem.alloc(shape, x.dtype)
+            views = self._kept[key]
+        else:
+            views = self._transient("gather", shape, x.dtype)
+        xs = x.view(self.B, rows // self.B, C)
+        for r in range(self.size):                      # own copy included: every rank ends up with all rows
+            self._rows(views[r], self.rank).copy_(xs)
+        self.mem.barrier()
+        return views[self.rank]
+
+    def _sum_slots(self, slots: torch.Tensor) -> torch.Tensor:
+        out = slots[0] + slots[1]
+        for r in range(2, self.size):
+            out += slots[r]
+        return out
+
+    def reduce_scatter(self, partial: torch.Tensor) -> torch.Tensor:
+        rows, C = partial.shape
+        Tl = rows // self.B // self.size
+        views = self._transient("rs", (self.size, self.B * Tl, C), partial.dtype)      # [source rank, local rows, C]
+        for r in range(self.size):
+            views[r][self.rank].view(self.B, Tl, C).copy_(self._rows(partial, r))
+        self.mem.barrier()
+        return self._sum_slots(views[self.rank])
+
+    def gemm_reduce_scatter(self, a: torch.Tensor, w: torch.Tensor, residual_s: torch.Tensor) -> torch.Tensor:
+        rows, K = a.shape
+        N = w.shape[0]
+        Tl = rows // self.B // self.size
+        views = self._transient("gemm_rs", (self.size, self.B * Tl, N), BF16)
+        res = residual_s.view(self.B, Tl, N)
+        # peers first: their tiles travel over NVLink while the local launch (which also adds the residual) computes
+        order = [r for r in range(self.size) if r != self.rank] + [self.rank]
+        for r in order:
+            a_r = self._rows(a, r)
+            slot = views[r][self.rank].view(self.B, Tl, N)
+            for b in range(self.B):
+                ops.gemm(a_r[b], w, out=slot[b], residual=res[b] if r == self.rank else None)
+        self.mem.barrier()
+        return self._sum_slots(views[self.rank])
+
+
+def make_context(group: dist.ProcessGroup, B: int, device: torch.device, cache_on=None) -> TPContext:
+    """TPContext of a model forward.  TN_TP_PEER=1 selects the NCCL-free PeerTPContext (cached on `cache_on`, it owns
+    symmetric buffers)."""
+    import os
+    if os.environ.get("TN_TP_PEER", "0") == "0":
+        return TPContext(group, B)
+    ctx = getattr(cache_on, "_tn_tp_peer_ctx", None) if cache_on is not None else None
+    if ctx is None or ctx.B != B or ctx.group is not group:
+        ctx = PeerTPContext(group, B, SymmPeerMemory(group, device))
+        if cache_on is not None:
+            cache_on._tn_tp_peer_ctx = ctx
+    return ctx

@@ -103,7 +103,26 @@ class AttnPlan:
         self.cp_group = None
         self.tp = None
         self.doc = doc_ids.to(torch.int32).contiguous()
-        self.meta = None
+        self.meta = _block_meta(self.doc)
+
+
+def _block_meta(doc):
+    """{kv_lo, kv_end, q_end, canonical} per 128-row block with the semantics of tn_attn_prep for canonical ids
+    (non-decreasing runs): kv_lo = block of the start of the document of the block's first valid row."""
+    B, T = doc.shape
+    nblk = (T + 127) // 128
+    meta = torch.zeros(B, nblk, 4, dtype=torch.int32)
+    for b in range(B):
+        d = doc[b].tolist()
+        for blk in range(nblk):
+            rows = [t for t in range(blk * 128, min(T, blk * 128 + 128)) if d[t] > 0]
+            if not rows:
+                continue
+            t = rows[0]
+            while t > 0 and d[t - 1] == d[rows[0]]:
+                t -= 1
+            meta[b, blk] = torch.tensor([t // 128, blk + 1, nblk, 1], dtype=torch.int32)
+    return meta.reshape(-1)
 
 
 def _mask(plan):
@@ -119,8 +138,15 @@ def _heads(x, B, rows, n):
     return x.float().reshape(B, rows, n, 128).permute(0, 2, 1, 3)
 
 
+def _finite(x):
+    """Rows the kernels never load may be uninitialised in the callers' buffers (context-parallel halo exchange); the dense
+    stand-in multiplies them by exact zeros, so make them finite first."""
+    return torch.nan_to_num(x.float(), nan=0.0, posinf=0.0, neginf=0.0)
+
+
 def attn_fwd(q, k, v, plan, H, KV, scale):
     B, T, Tq = plan.B, plan.T, plan.Tq
+    k, v = _finite(k), _finite(v)
     G = H // KV
     qh, kh, vh = _heads(q, B, Tq, H), _heads(k, B, T, KV).repeat_interleave(G, 1), _heads(v, B, T, KV).repeat_interleave(G, 1)
     s = (qh @ kh.transpose(-1, -2)) * scale
@@ -136,6 +162,7 @@ def attn_fwd(q, k, v, plan, H, KV, scale):
 
 def attn_bwd(q, k, v, o, do, lse, plan, H, KV, scale, out=None, rope=None):
     B, T, Tq = plan.B, plan.T, plan.Tq
+    k, v = _finite(k), _finite(v)
     G = H // KV
     qh, kh, vh = _heads(q, B, Tq, H), _heads(k, B, T, KV).repeat_interleave(G, 1), _heads(v, B, T, KV).repeat_interleave(G, 1)
     oh, doh = _heads(o, B, Tq, H), _heads(do, B, Tq, H)

@@ -162,7 +162,7 @@ def _tp_worker_peer(rank, world, port, q):
     _tp_worker(rank, world, port, True, True, q, peer=True)
 
 
-def _cp_worker(rank, world, port, q):
+def _cp_worker(rank, world, port, q, halo=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -172,6 +172,13 @@ def _cp_worker(rank, world, port, q):
         model, text = _build(False, False)
         B, T = 2, 256
         kw, doc, tgt = _inputs(B, T, text.vocab_size, False)
+        if halo:        # longer rows so that the halo is a strict subset of the neighbour's shard
+            os.environ["TN_CP_HALO"] = "1"
+            B, T = 2, 1024
+            g = torch.Generator().manual_seed(9)
+            doc, pos = _docs(B, T, [[300, 300, 300], [200, 400, 300]])
+            kw = dict(input_ids=torch.randint(1, text.vocab_size, (B, T), generator=g), attention_mask=doc, position_ids=pos)
+            tgt = torch.randn(B, T, text.vocab_size, generator=g)
         denom = float((doc > 0).sum()) * text.vocab_size
         ref_logits = model(**kw).logits
         _loss(ref_logits, tgt, doc, denom).backward()
@@ -180,6 +187,10 @@ def _cp_worker(rank, world, port, q):
         Tl = T // world
         sl = slice(rank * Tl, (rank + 1) * Tl)
         context_parallel.enable_context_parallel(model, dist.group.WORLD)
+        if halo:
+            plan = context_parallel.make_cp_plan(doc[:, sl].contiguous(), dist.group.WORLD)
+            assert context_parallel.halo_first_blocks(plan) == [0, 1]      # rank 1 needs rows 128.. of rank 0, not 0..
+            assert context_parallel._halo_pairs(plan) == [(0, 1, 128, 512)]
         lg = model(**{k: v[:, sl].contiguous() for k, v in kw.items()}).logits
         _loss(lg, tgt[:, sl], doc[:, sl], denom).backward()
         err_fwd = float((lg.float() - ref_logits[:, sl].float()).abs().max()) / float(ref_logits.float().abs().max())
@@ -235,6 +246,10 @@ def _tp_fsdp_worker(rank, world, port, q):
         q.put((rank, err_fwd, worst, worst_name))
     finally:
         dist.destroy_process_group()
+
+
+def _cp_worker_halo(rank, world, port, q):
+    _cp_worker(rank, world, port, q, halo=True)
 
 
 def _cp_fsdp_worker(rank, world, port, q):
@@ -323,6 +338,14 @@ def test_context_parallel_matches_unsharded():
 def test_tensor_parallel_composes_with_fsdp2():
     for rank, err_fwd, worst, name in _run(_tp_fsdp_worker, (), 30020, world=4):
         assert err_fwd < 2e-2, (rank, err_fwd)
+        assert worst < 3e-2, (rank, name, worst)
+
+
+def test_context_parallel_halo_exchange_matches_unsharded():
+    """TN_CP_HALO=1: only the K/V rows a rank's queries can reach are exchanged (here rows 128..511 of rank 0 instead of
+    its whole shard), dK/dV of those rows travel back; results equal the unsharded run."""
+    for rank, err_fwd, worst, name in _run(_cp_worker_halo, (), 30500):
+        assert err_fwd < 1e-2, (rank, err_fwd)
         assert worst < 3e-2, (rank, name, worst)
 
 

@@ -63,16 +63,123 @@ def _reduce_scatter_seq(x: torch.Tensor, B: int, group) -> torch.Tensor:
     return out.view(B * Tl, -1).to(x.dtype)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# halo exchange (EXPERIMENTAL, opt-in with TN_CP_HALO=1): move only the K/V rows a rank's queries can reach
+# ---------------------------------------------------------------------------------------------------------------
+# With packed documents a query never looks past the start of its own document, so rank r needs K/V only from the first
+# block of the earliest document that reaches into its window (the per-block `kv_lo` the attention kernels already use)
+# up to its own rows - typically a fraction of ONE neighbour's shard instead of every other rank's whole shard (SURVEY
+# 8(e): "halo exchange - an optimisation the reference does not do").  Same for dK/dV on the way back.  The exchanged
+# rows are whole 128-row blocks, so every block the kernels load is fully initialised.
+def _halo_enabled() -> bool:
+    import os
+    return os.environ.get("TN_CP_HALO", "0") != "0"
+
+
+def halo_first_blocks(plan: ops.AttnPlan) -> list:
+    """First K/V block each cp rank needs (<= its own first block), from the block metadata every rank holds.
+    One small device->host read per step, cached on the plan."""
+    cached = getattr(plan, "_halo_lo", None)
+    if cached is not None:
+        return cached
+    B, nblk = plan.B, (plan.T + 127) // 128
+    nq = plan.Tq // 128
+    cp = nblk // nq
+    m = plan.meta[: B * nblk * 4].view(B, nblk, 4)
+    kv_lo, kv_end = m[..., 0], m[..., 1]
+    lo = torch.where(kv_end > kv_lo, kv_lo, torch.full_like(kv_lo, nblk))      # padding-only blocks load nothing
+    lo = lo.view(B, cp, nq).amin(dim=(0, 2))
+    own = torch.arange(cp, device=lo.device, dtype=lo.dtype) * nq
+    plan._halo_lo = torch.minimum(lo, own).tolist()
+    return plan._halo_lo
+
+
+def _halo_pairs(plan: ops.AttnPlan):
+    """[(owner s, consumer r, first row, end row)]: rows of rank s that rank r > s needs (global row indices)."""
+    lo = halo_first_blocks(plan)
+    Tl = plan.Tq
+    out = []
+    for r in range(len(lo)):
+        for s in range(r):
+            a, b = max(lo[r] * 128, s * Tl), (s + 1) * Tl
+            if a < b:
+                out.append((s, r, a, b))
+    return out
+
+
+def _halo_gather(x: torch.Tensor, plan: ops.AttnPlan) -> torch.Tensor:
+    """[B*Tl, C] local rows -> [B*T, C] with this rank's rows and the halo rows it needs filled in (the rest of the
+    buffer is never read by the kernels)."""
+    group = plan.cp_group
+    me = dist.get_rank(group)
+    B, T, Tl = plan.B, plan.T, plan.Tq
+    C = x.shape[1]
+    full = torch.empty((B, T, C), dtype=x.dtype, device=x.device)
+    xl = x.view(B, Tl, C)
+    full[:, me * Tl:(me + 1) * Tl] = xl
+    reqs, recvs = [], []
+    for s, r, a, b in _halo_pairs(plan):
+        if me == s:
+            reqs.append(dist.P2POp(dist.isend, xl[:, a - s * Tl:b - s * Tl].contiguous(), dist.get_global_rank(group, r), group))
+        elif me == r:
+            buf = torch.empty((B, b - a, C), dtype=x.dtype, device=x.device)
+            recvs.append((buf, a, b))
+            reqs.append(dist.P2POp(dist.irecv, buf, dist.get_global_rank(group, s), group))
+    if reqs:
+        for w in dist.batch_isend_irecv(reqs):
+            w.wait()
+    for buf, a, b in recvs:
+        full[:, a:b] = buf
+    return full.view(B * T, C)
+
+
+def _halo_reduce(d_full: torch.Tensor, plan: ops.AttnPlan) -> torch.Tensor:
+    """[B*T, C] partial dK|dV (zero outside the rows this rank's queries reach) -> [B*Tl, C] summed rows of this rank:
+    halo rows go back to their owners (fp32 accumulation at the owner)."""
+    group = plan.cp_group
+    me = dist.get_rank(group)
+    B, T, Tl = plan.B, plan.T, plan.Tq
+    C = d_full.shape[1]
+    df = d_full.view(B, T, C)
+    reqs, recvs = [], []
+    for s, r, a, b in _halo_pairs(plan):
+        if me == r:
+            reqs.append(dist.P2POp(dist.isend, df[:, a:b].contiguous(), dist.get_global_rank(group, s), group))
+        elif me == s:
+            buf = torch.empty((B, b - a, C), dtype=d_full.dtype, device=d_full.device)
+            recvs.append((buf, a - s * Tl, b - s * Tl))
+            reqs.append(dist.P2POp(dist.irecv, buf, dist.get_global_rank(group, r), group))
+    if reqs:
+        for w in dist.batch_isend_irecv(reqs):
+            w.wait()
+    own = df[:, me * Tl:(me + 1) * Tl]
+    if not recvs:
+        return own.reshape(B * Tl, C).contiguous()
+    acc = own.float()
+    for buf, a, b in recvs:
+        acc[:, a:b] += buf.float()
+    return acc.to(d_full.dtype).view(B * Tl, C)
+
+
 def cp_attn_fwd(q, k, v, plan: ops.AttnPlan, H: int, KV: int, scale: float):
     """q [B*Tl, H*128] (already rotated), k/v [B*Tl, KV*128] local -> (o local, lse local, k_full, v_full)."""
-    kf = _gather_seq(k, plan.B, plan.cp_group)
-    vf = _gather_seq(v, plan.B, plan.cp_group)
+    if _halo_enabled():
+        kv = _halo_gather(torch.cat([k, v], dim=1), plan)          # one exchange for both; views keep the row stride
+        c = k.shape[1]
+        kf, vf = kv[:, :c], kv[:, c:]
+    else:
+        kf = _gather_seq(k, plan.B, plan.cp_group)
+        vf = _gather_seq(v, plan.B, plan.cp_group)
     o, lse = ops.attn_fwd(q, kf, vf, plan, H, KV, scale)
     return o, lse, kf, vf
 
 
 def cp_attn_bwd(q, kf, vf, o, do, lse, plan: ops.AttnPlan, H: int, KV: int, scale: float):
     dq, dk_full, dv_full = ops.attn_bwd(q, kf, vf, o, do, lse, plan, H, KV, scale)
+    if _halo_enabled():
+        c = dk_full.shape[1]
+        d = _halo_reduce(torch.cat([dk_full, dv_full], dim=1), plan)
+        return dq, d[:, :c].contiguous(), d[:, c:].contiguous()
     dk = _reduce_scatter_seq(dk_full, plan.B, plan.cp_group)
     dv = _reduce_scatter_seq(dv_full, plan.B, plan.cp_group)
     return dq, dk, dv

@@ -12,11 +12,20 @@ the reference's loop order: loss_fn and acc_fn run, `del pred`, then backward (r
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _lib
 
-_ARGMAX_CACHE: dict[int, tuple[int, torch.Tensor]] = {}
+# argmax of the logits the loss kernel saw last: (weak reference to the caller's logits tensor, its version, argmax).
+# Keyed on the live tensor OBJECT, not on its address - a freed tensor's address is reused by the next logits.
+_LAST_ARGMAX = None
+
+
+def _check_logits(logits: torch.Tensor) -> None:
+    if not logits.is_cuda or logits.dtype != torch.bfloat16:
+        raise _lib.TouchNetB200Error("pack-loss CE needs bf16 CUDA logits (no CPU path)")
 
 
 def _st() -> int:
@@ -26,8 +35,7 @@ def _st() -> int:
 class _PackCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, labels, sentence_lens, inv_num_sentence):
-        if not logits.is_cuda or logits.dtype != torch.bfloat16:
-            raise _lib.TouchNetB200Error("pack-loss CE needs bf16 CUDA logits (no CPU path)")
+        _check_logits(logits)
         V = logits.shape[-1]
         x = logits.view(-1, V)
         assert x.stride(1) == 1
@@ -39,18 +47,16 @@ class _PackCEFn(torch.autograd.Function):
         am = torch.empty(M, dtype=torch.int32, device=x.device)
         _lib.call("tn_pack_ce_fwd_bf16", x.data_ptr(), x.stride(0), lab.data_ptr(), lse.data_ptr(), ce.data_ptr(),
                   am.data_ptr(), M, V, _st())
-        _ARGMAX_CACHE.clear()
-        _ARGMAX_CACHE[x.data_ptr()] = (logits._version, am)
         ctx.save_for_backward(lab, sl, lse)
         ctx.logits = x                      # NOT save_for_backward: backward overwrites it in place on purpose
         ctx.inv_ns = inv_num_sentence
         ctx.shape = logits.shape
-        ctx.mark_non_differentiable(ce)
+        ctx.mark_non_differentiable(ce, am)
         loss_per_sample = (ce / sl.float()).sum() * inv_num_sentence
-        return loss_per_sample, ce
+        return loss_per_sample, ce, am
 
     @staticmethod
-    def backward(ctx, g_loss, _g_ce):
+    def backward(ctx, g_loss, _g_ce, _g_am):
         lab, sl, lse = ctx.saved_tensors
         x = ctx.logits
         g = g_loss.reshape(1).float().contiguous()
@@ -65,7 +71,9 @@ def cross_entropy_loss(pred: torch.Tensor, labels: torch.Tensor, sentence_lens: 
     """Same contract as ref: touchnet/loss/cross_entropy.py:12-50.  Returns (loss_per_sample, loss_per_token)."""
     assert ignore_index < 0, "labels outside [0, V) are ignored (the reference uses -100)"
     B = pred.shape[0]
-    loss_per_sample, ce = _PackCEFn.apply(pred, labels, sentence_lens, 1.0 / max(int(num_sentence), 1))
+    global _LAST_ARGMAX
+    loss_per_sample, ce, am = _PackCEFn.apply(pred, labels, sentence_lens, 1.0 / max(int(num_sentence), 1))
+    _LAST_ARGMAX = (weakref.ref(pred), pred._version, am)
     with torch.no_grad():
         num_tokens = (labels != ignore_index).sum()
         tot = ce.sum()
@@ -77,10 +85,11 @@ def accuracy(pred: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100)
     """Same contract as ref: touchnet/utils/metrics.py:26-50; reuses the argmax the loss kernel already produced."""
     V = pred.shape[-1]
     x = pred.view(-1, V)
-    ent = _ARGMAX_CACHE.get(x.data_ptr())
-    if ent is not None and ent[0] == pred._version:
-        am = ent[1]
+    ent = _LAST_ARGMAX
+    if ent is not None and ent[0]() is pred and ent[1] == pred._version and ent[2].numel() == x.shape[0]:
+        am = ent[2]
     else:
+        _check_logits(pred)
         M = x.shape[0]
         lse = torch.empty(M, dtype=torch.float32, device=x.device)
         ce = torch.empty_like(lse)

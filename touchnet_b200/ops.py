@@ -445,7 +445,10 @@ def rms_norm(x, w, eps):
 
 class PackedAttentionFn(torch.autograd.Function):
     """RoPE + block-causal document attention on projected q/k/v ([B*T, heads*128] GEMM outputs, rotated in place).
-    hf: apply_rotary_pos_emb :151-168 + flex_attention_forward (integrations/flex_attention.py:262-364)."""
+    hf: apply_rotary_pos_emb :151-168 + flex_attention_forward (integrations/flex_attention.py:262-364).
+    q and k are OVERWRITTEN with their rotated values: hand in tensors nothing else reads (the projection outputs; an
+    nn.Linear does not need its own output for backward).  The decoder block does not use this node (it fuses RoPE into
+    the QKV GEMM epilogue); it is the stand-alone form for callers that keep separate projections."""
 
     @staticmethod
     def forward(ctx, q, k, v, cos, sin, plan, H, KV, scale):

@@ -42,3 +42,22 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     assert "sm_100a" in sass or "SM100" in sass.upper()
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
         assert mnemonic in sass, mnemonic
+
+
+def test_ctypes_signatures_match_the_header_arity():
+    """Every prototype of include/touchnet_b200.h has a ctypes signature in touchnet_b200/_lib.py with the same number
+    of parameters (a drift here corrupts the call stack silently)."""
+    import os
+    import re
+    from touchnet_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "touchnet_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"\b(?:int|const char\*|int64_t)\s+(tn_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S)
+    assert len(protos) >= 30
+    for name, args in protos:
+        if name == "tn_last_error":
+            continue
+        n = 0 if args.strip() in ("void", "") else len(args.split(","))
+        assert name in _lib._SIGNATURES, f"{name} is declared in the header but has no ctypes signature"
+        assert len(_lib._SIGNATURES[name]) == n, (name, len(_lib._SIGNATURES[name]), n)
+    assert set(_lib._SIGNATURES) <= {p[0] for p in protos}, "ctypes signature without a header prototype"

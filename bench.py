@@ -435,6 +435,9 @@ def main():
         for i, layer in enumerate(layers):
             fully_shard(layer, mesh=mesh, mp_policy=mp, reshard_after_forward=(reshard and i < len(layers) - 1))
         fully_shard(model, mesh=mesh, mp_policy=mp, reshard_after_forward=reshard)
+        if os.environ.get("TN_FSDP_PEER", "0") != "0":   # EXPERIMENTAL: our pull kernels over NVLink peer memory instead of NCCL
+            from touchnet_b200 import fsdp_comm
+            fsdp_comm.install(model, mesh.get_group(), dev, max_ctas=int(os.environ.get("TN_FSDP_PEER_CTAS", "32")))
         depth = int(os.environ.get("TN_FSDP_PREFETCH", "0"))
         if depth > 0:                                    # explicit prefetch of the next `depth` blocks' all-gathers
             for i, layer in enumerate(layers):

@@ -223,6 +223,21 @@ int tn_pack_layout_i64(const int32_t* doc_row, const int32_t* doc_off, const int
                        int64_t eos, int64_t* input_ids, int64_t* labels, int64_t* position_ids, int64_t* attention_mask,
                        int64_t* sentence_lens, tn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Data-parallel collectives over NVLink peer memory (EXPERIMENTAL; SURVEY 8(e) "NCCL's or your own").  What FSDP2 does
+ * through NCCL around every decoder block (touchnet/models/helper_func.py:134-202: fp32 gradient reduce-scatter, bf16
+ * parameter all-gather) as pull kernels on buffers every rank has mapped (torch symmetric memory):
+ *   tn_peer_reduce_scatter_f32: out[i] = scale * sum_{p<n_peers} inputs[p][shard_offset + i], i < numel, summed in rank
+ *     order (bit-reproducible); inputs = HOST array of n_peers device pointers (peer-mapped), shard_offset % 4 == 0.
+ *   tn_peer_all_gather: out[p*bytes_each + j] = inputs[p][j]; bytes_each % 16 == 0.
+ * max_ctas bounds the grid (default 32) so that the GEMMs these overlap with keep their SMs.  Cross-rank ordering (inputs
+ * complete before the call, buffers not reused before every rank's call has finished) is the caller's barrier.
+ */
+int tn_peer_reduce_scatter_f32(const void* const* inputs, int n_peers, int64_t shard_offset, float* out, int64_t numel,
+                               float scale, int max_ctas, tn_stream_t stream);
+int tn_peer_all_gather(const void* const* inputs, int n_peers, int64_t bytes_each, void* out, int max_ctas,
+                       tn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

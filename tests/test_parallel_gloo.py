@@ -295,6 +295,76 @@ def _cp_fsdp_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _fsdp_peer_worker(rank, world, port, q):
+    """FSDP2=2 with touchnet_b200.fsdp_comm's peer-memory collectives plugged into every module group: the Comm
+    protocol (allocate / call), barrier placement and buffer ring against the unsharded model.  Symmetric memory ->
+    /dev/shm files, the two pull kernels -> torch on the mapped buffers."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ctypes
+        from tests import cpu_ops_shim
+        cpu_ops_shim.install()
+        from torch.distributed.device_mesh import init_device_mesh
+        from torch.distributed.fsdp import MixedPrecisionPolicy, fully_shard
+        from touchnet_b200 import fsdp_comm
+
+        def at(ptr, n, dtype):
+            es = torch.empty(0, dtype=dtype).element_size()
+            return torch.frombuffer((ctypes.c_char * (n * es)).from_address(ptr), dtype=dtype)
+
+        calls = {"rs": 0, "ag": 0}
+
+        def fake_rs(ptrs, shard_offset, out, numel, scale, max_ctas):
+            calls["rs"] += 1
+            acc = at(ptrs[0] + 4 * shard_offset, numel, torch.float32).clone()
+            for p in ptrs[1:]:
+                acc += at(p + 4 * shard_offset, numel, torch.float32)
+            out.view(-1).copy_(acc * scale)
+
+        def fake_ag(ptrs, bytes_each, out, max_ctas):
+            calls["ag"] += 1
+            o = out.view(-1).view(torch.uint8)
+            for i, p in enumerate(ptrs):
+                o[i * bytes_each:(i + 1) * bytes_each] = at(p, bytes_each, torch.uint8)
+
+        fsdp_comm._launch_reduce_scatter, fsdp_comm._launch_all_gather = fake_rs, fake_ag
+        model, text = _build(False, False)
+        B, T = 2, 256
+        kw, doc, tgt = _inputs(B, T, text.vocab_size, False)
+        denom = float((doc > 0).sum()) * text.vocab_size
+        ref_model = copy.deepcopy(model)
+        ref_logits = ref_model(**kw).logits
+        _loss(ref_logits, tgt, doc, denom).backward()
+        ref_grads = {n: p.grad.clone() for n, p in ref_model.named_parameters()}
+
+        mesh = init_device_mesh("cpu", (world,), mesh_dim_names=("dp_shard",))
+        mp_policy = MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.float32)
+        for layer in model.model.layers:
+            fully_shard(layer, mesh=mesh, mp_policy=mp_policy)
+        fully_shard(model, mesh=mesh, mp_policy=mp_policy)
+        mem = FilePeerMemory(mesh.get_group(), "cpu")
+        pool = fsdp_comm.install(model, mesh.get_group(), "cpu", mem=mem)
+        row = slice(rank, rank + 1)
+        worst, worst_name, err_fwd = 0.0, "", 0.0
+        for step in range(2):                                             # second step reuses the ring buffers
+            model.zero_grad()
+            logits = model(**{k: v[row] for k, v in kw.items()}).logits
+            _loss(logits, tgt[row], doc[row], denom).backward()
+            err_fwd = max(err_fwd, float((logits.float() - ref_logits[row].float())[doc[row] > 0].abs().max())
+                          / float(ref_logits.float().abs().max()))
+            for n, p in model.named_parameters():
+                e = _rel(p.grad.full_tensor().float() * world, ref_grads[n].float())
+                if e > worst:
+                    worst, worst_name = e, n
+        assert calls["rs"] == 2 * 3 and calls["ag"] >= 2 * 3, calls      # 2 blocks + root, every step
+        assert all(len(r) <= fsdp_comm.RING for r in pool._rings.values())
+        mem.cleanup()
+        q.put((rank, err_fwd, worst, worst_name))
+    finally:
+        dist.destroy_process_group()
+
+
 def _run(target, args, port_base, world=2):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -352,4 +422,10 @@ def test_context_parallel_halo_exchange_matches_unsharded():
 def test_context_parallel_composes_with_fsdp2():
     for rank, err_fwd, worst, name in _run(_cp_fsdp_worker, (), 30180, world=4):
         assert err_fwd < 1e-2, (rank, err_fwd)
+        assert worst < 3e-2, (rank, name, worst)
+
+
+def test_fsdp2_peer_memory_collectives_match_unsharded():
+    for rank, err_fwd, worst, name in _run(_fsdp_peer_worker, (), 30660):
+        assert err_fwd < 2e-2, (rank, err_fwd)
         assert worst < 3e-2, (rank, name, worst)

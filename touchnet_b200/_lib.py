@@ -47,6 +47,8 @@ _SIGNATURES = {
     "tn_pack_ce_fwd_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _vp],
     "tn_pack_ce_bwd_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _f, _i64, _i, _vp],
     "tn_pack_layout_i64": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tn_peer_reduce_scatter_f32": [_vp, _i, _i64, _vp, _i64, _f, _i, _vp],
+    "tn_peer_all_gather": [_vp, _i, _i64, _vp, _i, _vp],
     "tn_sumsq_num_partials": [],
     "tn_sumsq_f32": [_vp, _i64, _vp, _vp, _vp],
     "tn_scale_f32": [_vp, _i64, _vp, _vp],

@@ -1,0 +1,148 @@
+"""FSDP2 collectives over NVLink peer memory with our own kernels (EXPERIMENTAL groundwork, opt-in).
+
+FSDP2 (ref: touchnet/models/helper_func.py:134-202) lets a module group swap its communication primitives
+(`FSDPModule.set_custom_reduce_scatter / set_custom_all_gather`, torch/distributed/fsdp/_fully_shard/_fsdp_api.py).
+`PeerReduceScatter` / `PeerAllGather` allocate FSDP2's communication buffers in symmetric memory (every rank maps every
+rank's buffer, CUDA IPC over NVLink) and replace the NCCL ring kernels by one pull kernel each
+(csrc/collective.cu: tn_peer_reduce_scatter_f32 / tn_peer_all_gather) between two device-side barriers' worth of ordering:
+
+    reduce-scatter   barrier (every rank's gradient copy-in is complete)  ->  out = 1/N * sum_p in_p[my shard]
+    all-gather       barrier (every rank's shard copy-in is complete)     ->  out[p] = in_p[p's shard]  for all p
+
+Why: at N=2 the NCCL reduce-scatter (ring, LL protocol) is busy 79 ms of a 407 ms step and slows the backward GEMMs it
+overlaps by 17 %; a pull of 8 GB over NVLink is ~12 ms of a few CTAs.  Buffers come from a ring of three
+per size: a buffer is rewritten only after later barriers which every reader reaches after its pull (stream order; FSDP2
+itself orders the next copy-in behind the previous collective of the same kind).  To be confirmed on hardware: that
+ordering across FSDP2's copy-in / collective streams, and the SM budget (`max_ctas`).
+
+STATUS: written at the end of round 1 after the GPU minutes were spent.  The Comm plumbing (allocate / call protocol,
+barrier placement, buffer ring) is verified on CPU with FSDP2 over gloo, shared-memory files standing in for symmetric
+memory and torch standing in for the two kernels (tests/test_parallel_gloo.py); it has NOT run on hardware.  Opt-in:
+`fsdp_comm.install(model, mesh)` after `fully_shard`, or TN_FSDP_PEER=1 for bench.py.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+from torch.distributed.fsdp._fully_shard._fsdp_api import AllGather, ReduceScatter
+
+from . import _lib
+
+RING = 3        # FSDP2 keeps at most two buffers of a kind alive (current + prefetched); one spare
+
+
+def _launch_reduce_scatter(ptrs: list, shard_offset: int, out: torch.Tensor, numel: int, scale: float, max_ctas: int) -> None:
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    _lib.call("tn_peer_reduce_scatter_f32", arr, len(ptrs), shard_offset, out.data_ptr(), numel, float(scale), max_ctas,
+              torch.cuda.current_stream().cuda_stream)
+
+
+def _launch_all_gather(ptrs: list, bytes_each: int, out: torch.Tensor, max_ctas: int) -> None:
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    _lib.call("tn_peer_all_gather", arr, len(ptrs), bytes_each, out.data_ptr(), max_ctas,
+              torch.cuda.current_stream().cuda_stream)
+
+
+class _PeerPool:
+    """Symmetric communication buffers of one process group, handed out FSDP2-style through `allocate`."""
+
+    def __init__(self, group: dist.ProcessGroup, device, mem=None):
+        from .tensor_parallel import SymmPeerMemory
+        self.group = group
+        self.size, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.mem = mem if mem is not None else SymmPeerMemory(group, torch.device(device))
+        self._rings: dict = {}       # (numel, dtype) -> [list of per-rank views] * RING
+        self._next: dict = {}
+        self._by_ptr: dict = {}      # data_ptr of this rank's buffer -> per-rank views
+
+    def allocate(self, size: Sequence[int], *, dtype: torch.dtype, device) -> torch.Tensor:
+        numel = math.prod(int(s) for s in size)
+        key = (numel, dtype)
+        ring = self._rings.setdefault(key, [])
+        i = self._next.get(key, 0)
+        if i >= len(ring):
+            if len(ring) < RING:
+                views = self.mem.alloc((numel,), dtype)          # collective: every rank allocates in the same order
+                ring.append(views)
+                self._by_ptr[views[self.rank].data_ptr()] = views
+            else:
+                i = 0
+        self._next[key] = (i + 1) % RING if len(ring) == RING else i + 1
+        return ring[i][self.rank].view(*[int(s) for s in size])
+
+    def views_of(self, t: torch.Tensor) -> list:
+        v = self._by_ptr.get(t.data_ptr())
+        if v is None:
+            raise _lib.TouchNetB200Error("peer collective called on a buffer that did not come from its allocate()")
+        return v
+
+
+class PeerReduceScatter(ReduceScatter):
+    """fp32 gradient reduce-scatter of one FSDP2 group as a pull over peer memory (SUM or AVG)."""
+
+    def __init__(self, pool: _PeerPool, max_ctas: int = 32):
+        self.pool, self.max_ctas = pool, max_ctas
+
+    def allocate(self, size, *, dtype, device) -> torch.Tensor:
+        return self.pool.allocate(size, dtype=dtype, device=device)
+
+    def __call__(self, output_tensor, input_tensor, group, op, async_op: bool = False):
+        if input_tensor.dtype != torch.float32:
+            raise _lib.TouchNetB200Error("PeerReduceScatter handles fp32 gradients (reduce_dtype=float32, the reference's default)")
+        pool = self.pool
+        n = output_tensor.numel()
+        if input_tensor.numel() != n * pool.size:
+            raise _lib.TouchNetB200Error("reduce-scatter input must be world_size x output")
+        if op == dist.ReduceOp.AVG:
+            scale = 1.0 / pool.size
+        elif op == dist.ReduceOp.SUM:
+            scale = 1.0
+        else:
+            raise _lib.TouchNetB200Error(f"PeerReduceScatter: unsupported reduce op {op}")
+        views = pool.views_of(input_tensor)
+        pool.mem.barrier()                                       # every rank's copy-in of this group has completed
+        _launch_reduce_scatter([v.data_ptr() for v in views], pool.rank * n, output_tensor, n, scale, self.max_ctas)
+        return None                                              # stream-ordered on the caller's (reduce-scatter) stream
+
+
+class PeerAllGather(AllGather):
+    """bf16 (or fp32) parameter all-gather of one FSDP2 group as a pull over peer memory.  FSDP2 gathers in place: the
+    input is this rank's slice of the output buffer, so every rank's shard already sits in its own symmetric buffer."""
+
+    def __init__(self, pool: _PeerPool, max_ctas: int = 32):
+        self.pool, self.max_ctas = pool, max_ctas
+
+    def allocate(self, size, *, dtype, device) -> torch.Tensor:
+        return self.pool.allocate(size, dtype=dtype, device=device)
+
+    def __call__(self, output_tensor, input_tensor, group, async_op: bool = False):
+        pool = self.pool
+        n = input_tensor.numel()
+        es = input_tensor.element_size()
+        if output_tensor.numel() != n * pool.size or (n * es) % 16 != 0:
+            raise _lib.TouchNetB200Error("all-gather output must be world_size x input, shard bytes a multiple of 16")
+        views = pool.views_of(output_tensor)
+        if input_tensor.data_ptr() != output_tensor.data_ptr() + pool.rank * n * es:
+            output_tensor.view(-1)[pool.rank * n:(pool.rank + 1) * n].copy_(input_tensor.reshape(-1))
+        pool.mem.barrier()                                       # every rank's shard is in its own buffer
+        ptrs = [views[p].data_ptr() + p * n * es for p in range(pool.size)]
+        _launch_all_gather(ptrs, n * es, output_tensor, self.max_ctas)
+        return None
+
+
+def install(model: torch.nn.Module, group: dist.ProcessGroup, device, mem=None, all_gather: bool = True,
+            reduce_scatter: bool = True, max_ctas: int = 32) -> _PeerPool:
+    """Give every FSDP2 module group of `model` the peer-memory collectives (call after `fully_shard`)."""
+    from torch.distributed.fsdp import FSDPModule
+    pool = _PeerPool(group, device, mem)
+    for m in model.modules():
+        if isinstance(m, FSDPModule):
+            if reduce_scatter:
+                m.set_custom_reduce_scatter(PeerReduceScatter(pool, max_ctas))
+            if all_gather:
+                m.set_custom_all_gather(PeerAllGather(pool, max_ctas))
+    return pool

@@ -19,12 +19,14 @@ def test_peer_reduce_scatter(n_peers, shard, avg):
     ins = [torch.randn(n_peers * shard, generator=g).to(dev) for _ in range(n_peers)]
     scale = 1.0 / n_peers if avg else 1.0
     for rank in range(n_peers):
-        out = torch.full((shard,), float("nan"), device=dev)
-        fsdp_comm._launch_reduce_scatter([t.data_ptr() for t in ins], rank * shard, out, shard, scale, 32)
-        acc = ins[0][rank * shard:(rank + 1) * shard].clone()
-        for t in ins[1:]:
-            acc += t[rank * shard:(rank + 1) * shard]
-        assert torch.equal(out, acc * scale), (n_peers, shard, rank)
+        for numel in (shard, shard - 3):                  # shard - 3: exercises the scalar tail (numel % 4 != 0)
+            out = torch.full((shard,), float("nan"), device=dev)
+            fsdp_comm._launch_reduce_scatter([t.data_ptr() for t in ins], rank * shard, out, numel, scale, 32)
+            acc = ins[0][rank * shard:rank * shard + numel].clone()
+            for t in ins[1:]:
+                acc += t[rank * shard:rank * shard + numel]
+            assert torch.equal(out[:numel], acc * scale), (n_peers, shard, rank, numel)
+            assert torch.isnan(out[numel:]).all()          # nothing written past the requested range
 
 
 @pytest.mark.parametrize("n_peers,n", [(2, 1 << 20), (4, 4096 + 8), (8, 1000 * 8)])

@@ -162,7 +162,7 @@ def _tp_worker_peer(rank, world, port, q):
     _tp_worker(rank, world, port, True, True, q, peer=True)
 
 
-def _cp_worker(rank, world, port, q, halo=False):
+def _cp_worker(rank, world, port, q, halo=False, head_tail=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -172,8 +172,9 @@ def _cp_worker(rank, world, port, q, halo=False):
         model, text = _build(False, False)
         B, T = 2, 256
         kw, doc, tgt = _inputs(B, T, text.vocab_size, False)
-        if halo:        # longer rows so that the halo is a strict subset of the neighbour's shard
-            os.environ["TN_CP_HALO"] = "1"
+        if halo or head_tail:   # longer rows: the halo is a strict subset of the neighbour's shard / four chunks of 256
+            if halo:
+                os.environ["TN_CP_HALO"] = "1"
             B, T = 2, 1024
             g = torch.Generator().manual_seed(9)
             doc, pos = _docs(B, T, [[300, 300, 300], [200, 400, 300]])
@@ -186,7 +187,11 @@ def _cp_worker(rank, world, port, q, halo=False):
         model.zero_grad()
         Tl = T // world
         sl = slice(rank * Tl, (rank + 1) * Tl)
-        context_parallel.enable_context_parallel(model, dist.group.WORLD)
+        if head_tail:           # torch's load-balanced layout: chunk r followed by chunk 2*cp-1-r
+            Tw = Tl // 2
+            sl = torch.cat([torch.arange(rank * Tw, (rank + 1) * Tw),
+                            torch.arange((2 * world - 1 - rank) * Tw, (2 * world - rank) * Tw)])
+        context_parallel.enable_context_parallel(model, dist.group.WORLD, load_balance=head_tail)
         if halo:
             plan = context_parallel.make_cp_plan(doc[:, sl].contiguous(), dist.group.WORLD)
             assert context_parallel.halo_first_blocks(plan) == [0, 1]      # rank 1 needs rows 128.. of rank 0, not 0..
@@ -250,6 +255,10 @@ def _tp_fsdp_worker(rank, world, port, q):
 
 def _cp_worker_halo(rank, world, port, q):
     _cp_worker(rank, world, port, q, halo=True)
+
+
+def _cp_worker_head_tail(rank, world, port, q):
+    _cp_worker(rank, world, port, q, head_tail=True)
 
 
 def _cp_fsdp_worker(rank, world, port, q):
@@ -415,6 +424,15 @@ def test_context_parallel_halo_exchange_matches_unsharded():
     """TN_CP_HALO=1: only the K/V rows a rank's queries can reach are exchanged (here rows 128..511 of rank 0 instead of
     its whole shard), dK/dV of those rows travel back; results equal the unsharded run."""
     for rank, err_fwd, worst, name in _run(_cp_worker_halo, (), 30500):
+        assert err_fwd < 1e-2, (rank, err_fwd)
+        assert worst < 3e-2, (rank, name, worst)
+
+
+def test_context_parallel_head_tail_layout_matches_unsharded():
+    """load_balance=True: the sequence shards arrive in torch's head-tail order (rank r = chunk r + chunk 2cp-1-r, what
+    `context_parallel` hands the model by default); two query windows per rank, K/V and dK/dV re-ordered around the
+    collectives; results equal the unsharded run."""
+    for rank, err_fwd, worst, name in _run(_cp_worker_head_tail, (), 30820):
         assert err_fwd < 1e-2, (rank, err_fwd)
         assert worst < 3e-2, (rank, name, worst)
 

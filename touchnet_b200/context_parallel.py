@@ -25,39 +25,81 @@ import torch.distributed as dist
 from . import ops
 
 
-def make_cp_plan(local_doc_ids: torch.Tensor, group: Optional[dist.ProcessGroup]) -> ops.AttnPlan:
+def make_cp_plan(local_doc_ids: torch.Tensor, group: Optional[dist.ProcessGroup], load_balance: bool = False) -> ops.AttnPlan:
     """All-gather the (tiny) per-rank document-id slices into the global [B, T] ids and build the attention plan of this
-    rank's query window.  local_doc_ids: [B, T/cp] (the `attention_mask` buffer as the reference shards it)."""
+    rank's query window(s).  local_doc_ids: [B, T/cp] (the `attention_mask` buffer as the reference shards it).
+
+    load_balance=False: rank r holds the contiguous rows [r*T/cp, (r+1)*T/cp).
+    load_balance=True : torch's head-tail layout (the default of `context_parallel`, _HeadTailLoadBalancer): the sequence
+                        is cut into 2*cp chunks and rank r holds chunk r followed by chunk 2*cp-1-r, so that every rank
+                        gets the same causal work; the attention kernels then run once per chunk (two query windows)."""
     cp = dist.get_world_size(group)
     rank = dist.get_rank(group)
     B, Tl = local_doc_ids.shape
-    if Tl % 128 != 0:
-        raise ops._lib.TouchNetB200Error(f"context parallelism needs T/cp to be a multiple of 128, got {Tl}")
+    unit = 256 if load_balance else 128
+    if Tl % unit != 0:
+        raise ops._lib.TouchNetB200Error(f"context parallelism needs T/cp to be a multiple of {unit}, got {Tl}")
     ids = local_doc_ids.to(torch.int32).contiguous()
     parts = [torch.empty_like(ids) for _ in range(cp)]
     dist.all_gather(parts, ids, group=group)
-    full = torch.cat(parts, dim=1)
-    plan = ops.AttnPlan(full, Tq=Tl, q_blk_off=rank * Tl // 128)
+    if not load_balance:
+        full = torch.cat(parts, dim=1)
+        plan = ops.AttnPlan(full, Tq=Tl, q_blk_off=rank * Tl // 128)
+        plan.cp_group = group
+        return plan
+    Tw = Tl // 2
+    full = _head_tail_to_global(torch.stack(parts).unsqueeze(-1), B).view(B, cp * Tl)
+    plan = ops.AttnPlan(full, Tq=Tw, q_blk_off=rank * Tw // 128)
     plan.cp_group = group
+    plan.cp_windows = [rank * Tw // 128, (2 * cp - 1 - rank) * Tw // 128]      # first block of each local chunk
     return plan
 
 
-def _gather_seq(x: torch.Tensor, B: int, group) -> torch.Tensor:
+def _head_tail_to_global(g: torch.Tensor, B: int) -> torch.Tensor:
+    """[cp, B, Tl, C] per-rank head-tail shards -> [B*T, C] in global sequence order."""
+    cp, _, Tl, C = g.shape
+    Tw = Tl // 2
+    out = torch.empty((B, 2 * cp, Tw, C), dtype=g.dtype, device=g.device)
+    gv = g.view(cp, B, 2, Tw, C)
+    for r in range(cp):
+        out[:, r] = gv[r, :, 0]
+        out[:, 2 * cp - 1 - r] = gv[r, :, 1]
+    return out.view(B * 2 * cp * Tw, C)
+
+
+def _global_to_head_tail(x: torch.Tensor, B: int, cp: int) -> torch.Tensor:
+    """[B*T, C] global order -> [cp, B, Tl, C]: slot r = what rank r holds (chunk r, then chunk 2*cp-1-r)."""
+    C = x.shape[-1]
+    Tw = x.shape[0] // B // (2 * cp)
+    xv = x.view(B, 2 * cp, Tw, C)
+    out = torch.empty((cp, B, 2, Tw, C), dtype=x.dtype, device=x.device)
+    for r in range(cp):
+        out[r, :, 0] = xv[:, r]
+        out[r, :, 1] = xv[:, 2 * cp - 1 - r]
+    return out.view(cp, B, 2 * Tw, C)
+
+
+def _gather_seq(x: torch.Tensor, B: int, group, head_tail: bool = False) -> torch.Tensor:
     """[B*Tl, C] local rows -> [B*T, C] global rows (sequence-contiguous per batch row)."""
     cp = dist.get_world_size(group)
     Tl = x.shape[0] // B
     xs = x.contiguous()
     out = torch.empty((cp * xs.shape[0],) + tuple(xs.shape[1:]), dtype=xs.dtype, device=xs.device)
     dist.all_gather_into_tensor(out, xs, group=group)
+    if head_tail:
+        return _head_tail_to_global(out.view(cp, B, Tl, -1), B)
     return out.view(cp, B, Tl, -1).permute(1, 0, 2, 3).reshape(B * cp * Tl, -1)
 
 
-def _reduce_scatter_seq(x: torch.Tensor, B: int, group) -> torch.Tensor:
+def _reduce_scatter_seq(x: torch.Tensor, B: int, group, head_tail: bool = False) -> torch.Tensor:
     """[B*T, C] partial sums over global rows -> [B*Tl, C] summed rows of this rank (fp32 accumulation on the wire)."""
     cp = dist.get_world_size(group)
     T = x.shape[0] // B
     Tl = T // cp
-    xs = x.view(B, cp, Tl, -1).permute(1, 0, 2, 3).contiguous().float().view(cp * B * Tl, -1)
+    if head_tail:
+        xs = _global_to_head_tail(x, B, cp).float().view(cp * B * Tl, -1)
+    else:
+        xs = x.view(B, cp, Tl, -1).permute(1, 0, 2, 3).contiguous().float().view(cp * B * Tl, -1)
     out = torch.empty((B * Tl, xs.shape[-1]), dtype=torch.float32, device=x.device)
     dist.reduce_scatter_tensor(out, xs, op=dist.ReduceOp.SUM, group=group)
     return out.view(B * Tl, -1).to(x.dtype)
@@ -161,8 +203,55 @@ def _halo_reduce(d_full: torch.Tensor, plan: ops.AttnPlan) -> torch.Tensor:
     return acc.to(d_full.dtype).view(B * Tl, C)
 
 
+def _window_plan(plan: ops.AttnPlan, q_blk_off: int) -> ops.AttnPlan:
+    import copy
+    pw = copy.copy(plan)                  # shares the document ids / block metadata, differs in the query window
+    pw.q_blk_off = q_blk_off
+    return pw
+
+
+def _window_rows(x: torch.Tensor, B: int, w: int) -> torch.Tensor:
+    """Rows of local chunk w (0 = head, 1 = tail) of a [B*2*Tw, C] tensor as a dense [B*Tw, C] tensor."""
+    C = x.shape[-1]
+    Tw = x.shape[0] // B // 2
+    xw = x.view(B, 2, Tw, C)[:, w]
+    return xw.reshape(B * Tw, C) if B == 1 else xw.contiguous().view(B * Tw, C)
+
+
+def _cp_attn_fwd_head_tail(q, k, v, plan, H, KV, scale):
+    B = plan.B
+    kf = _gather_seq(k, B, plan.cp_group, head_tail=True)
+    vf = _gather_seq(v, B, plan.cp_group, head_tail=True)
+    Tw = plan.Tq
+    o = torch.empty((B, 2, Tw, q.shape[1]), dtype=q.dtype, device=q.device)
+    lses = []
+    for w, off in enumerate(plan.cp_windows):
+        o_w, lse_w = ops.attn_fwd(_window_rows(q, B, w), kf, vf, _window_plan(plan, off), H, KV, scale)
+        o[:, w] = o_w.view(B, Tw, -1)
+        lses.append(lse_w)
+    return o.view(B * 2 * Tw, -1), torch.cat(lses, dim=-1), kf, vf
+
+
+def _cp_attn_bwd_head_tail(q, kf, vf, o, do, lse, plan, H, KV, scale):
+    B, Tw = plan.B, plan.Tq
+    dq = torch.empty((B, 2, Tw, q.shape[1]), dtype=q.dtype, device=q.device)
+    dk_full = dv_full = None
+    for w, off in enumerate(plan.cp_windows):
+        lse_w = lse[..., w * Tw:(w + 1) * Tw].contiguous()
+        dq_w, dk_w, dv_w = ops.attn_bwd(_window_rows(q, B, w), kf, vf, _window_rows(o, B, w), _window_rows(do, B, w),
+                                        lse_w, _window_plan(plan, off), H, KV, scale)
+        dq[:, w] = dq_w.view(B, Tw, -1)
+        dk_full = dk_w.float() if dk_full is None else dk_full + dk_w.float()
+        dv_full = dv_w.float() if dv_full is None else dv_full + dv_w.float()
+    dk = _reduce_scatter_seq(dk_full, B, plan.cp_group, head_tail=True)
+    dv = _reduce_scatter_seq(dv_full, B, plan.cp_group, head_tail=True)
+    return dq.view(B * 2 * Tw, -1), dk.to(q.dtype), dv.to(q.dtype)
+
+
 def cp_attn_fwd(q, k, v, plan: ops.AttnPlan, H: int, KV: int, scale: float):
     """q [B*Tl, H*128] (already rotated), k/v [B*Tl, KV*128] local -> (o local, lse local, k_full, v_full)."""
+    if getattr(plan, "cp_windows", None) is not None:
+        return _cp_attn_fwd_head_tail(q, k, v, plan, H, KV, scale)
     if _halo_enabled():
         kv = _halo_gather(torch.cat([k, v], dim=1), plan)          # one exchange for both; views keep the row stride
         c = k.shape[1]
@@ -175,6 +264,8 @@ def cp_attn_fwd(q, k, v, plan: ops.AttnPlan, H: int, KV: int, scale: float):
 
 
 def cp_attn_bwd(q, kf, vf, o, do, lse, plan: ops.AttnPlan, H: int, KV: int, scale: float):
+    if getattr(plan, "cp_windows", None) is not None:
+        return _cp_attn_bwd_head_tail(q, kf, vf, o, do, lse, plan, H, KV, scale)
     dq, dk_full, dv_full = ops.attn_bwd(q, kf, vf, o, do, lse, plan, H, KV, scale)
     if _halo_enabled():
         c = dk_full.shape[1]
@@ -185,11 +276,14 @@ def cp_attn_bwd(q, kf, vf, o, do, lse, plan: ops.AttnPlan, H: int, KV: int, scal
     return dq, dk, dv
 
 
-def enable_context_parallel(model: torch.nn.Module, group: Optional[dist.ProcessGroup]) -> None:
+def enable_context_parallel(model: torch.nn.Module, group: Optional[dist.ProcessGroup], load_balance: bool = False) -> None:
     """Mark a B200LlamaForCausalLM / B200TouchAudioForCausalLM as running on sequence shards of the given cp group
     (pass None to switch it off).  The caller feeds every per-token buffer already sharded on dim 1, as the reference's
-    `create_context_parallel_ctx` does (ref: touchnet/bin/train.py:363-387)."""
+    `create_context_parallel_ctx` does (ref: touchnet/bin/train.py:363-387): contiguous shards by default,
+    load_balance=True for torch's head-tail layout (what `context_parallel` produces unless its load balancing is
+    switched off)."""
     from . import modeling
     for m in model.modules():
         if isinstance(m, modeling.B200LlamaModel):
             m.cp_group = group
+            m.cp_load_balance = bool(load_balance)

@@ -205,7 +205,7 @@ class B200LlamaModel(nn.Module):
         cp_group = getattr(self, "cp_group", None)
         if cp_group is not None:                            # sequence sharded over the cp mesh: see context_parallel.py
             from . import context_parallel
-            plan = context_parallel.make_cp_plan(attention_mask, cp_group)
+            plan = context_parallel.make_cp_plan(attention_mask, cp_group, getattr(self, "cp_load_balance", False))
         else:
             plan = ops.AttnPlan(attention_mask)             # once per step, shared by all layers
         if tp_group is not None:

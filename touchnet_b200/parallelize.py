@@ -6,7 +6,8 @@ Order as in the reference: tensor parallel -> (activation checkpointing) -> FSDP
 * tp  -> touchnet_b200.tensor_parallel.apply_tp: the reference's `parallelize_module` plan hooks nn.Linear.forward, which
          the fused decoder block never calls, so the same sharding is applied to the parameters and the collectives run
          inside the block.
-* cp  -> touchnet_b200.context_parallel.enable_context_parallel on the `cp` sub-mesh.
+* cp  -> touchnet_b200.context_parallel.enable_context_parallel on the `cp` sub-mesh, in the shard layout torch's
+         `context_parallel` context will produce (head-tail load balancing on by default, contiguous when switched off).
 * dp  -> FSDP2 per decoder block + root, same mixed-precision / reshard policies as ref helper_func.py:134-202.  When the
          reference package is importable its own parallelize function does this part (it also owns AC / compile / DDP);
          it is handed a view of `parallel_dims` with tp switched off so that it does not re-apply its DTensor plan.
@@ -32,6 +33,16 @@ class _WithoutTP:
         if name == "tp_enabled":
             return False
         return getattr(self._dims, name)
+
+
+def _torch_cp_load_balance() -> bool:
+    """Whether the train loop's `context_parallel` context (ref: touchnet/utils/distributed.py:292-315) will hand the model
+    head-tail load-balanced sequence shards (torch's default) or contiguous ones."""
+    try:
+        from torch.distributed.tensor.experimental._attention import _cp_options
+        return bool(_cp_options.enable_load_balance)
+    except Exception:
+        return False
 
 
 def apply_fsdp(model: torch.nn.Module, dp_mesh, param_dtype=torch.bfloat16, reduce_dtype=torch.float32,
@@ -66,7 +77,7 @@ def make_parallelize_fn(base_fn: Optional[Callable] = None) -> Callable:
         if getattr(parallel_dims, "tp_enabled", False):
             tensor_parallel.apply_tp(model, world_mesh["tp"])
         if getattr(parallel_dims, "cp_enabled", False):
-            context_parallel.enable_context_parallel(model, world_mesh["cp"].get_group())
+            context_parallel.enable_context_parallel(model, world_mesh["cp"].get_group(), load_balance=_torch_cp_load_balance())
         if base_fn is not None:
             return base_fn(model, world_mesh, _WithoutTP(parallel_dims), job_config)
         if getattr(parallel_dims, "dp_shard_enabled", False) or getattr(parallel_dims, "cp_enabled", False):

@@ -5,4 +5,5 @@ __version__ = "0.1.0"
 
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "ops", "modeling", "frontend", "batching", "train_spec"]
+__all__ = ["_lib", "ops", "modeling", "frontend", "batching", "loss", "tokenizer", "optim", "train_spec", "parallelize",
+           "tensor_parallel", "context_parallel", "fsdp_comm"]

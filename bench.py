@@ -247,6 +247,48 @@ def attn_flops_fwd_per_layer(doc_lens, H=32, hd=128):
     return 4.0 * H * hd * sum(n * (n + 1) / 2 for n in doc_lens)
 
 
+def derived_columns(by_class: dict, steps: int, ms_per_step: float, attn_fwd_flop_step: float, nonpad_tokens: int,
+                    tokens_per_step: int, B: int, T: int, layers: int, peaks: dict, text: dict) -> dict:
+    """The report columns of BASELINE.md (attention TFLOP/s and MFU, HBM GB/s of the norm / SwiGLU-backward / loss kernels,
+    non-pad tokens/s, the reference's own MFU convention) from the per-entry-point device times of the timed region.
+    rank 0's rows; never raises (a missing key only drops its column)."""
+    out = {}
+    try:
+        per = {k: v / steps for k, v in by_class.items()}              # ms per step
+        peak = float(peaks["bf16_sustained"])
+        rows, d, ffn, V = B * T, text["hidden_size"], text["intermediate_size"], text["vocab_size"]
+        out["nonpad_tokens_per_s_rank0"] = nonpad_tokens / (ms_per_step * 1e-3)
+        if per.get("tn_attn_fwd_bf16"):
+            tf = attn_fwd_flop_step / (per["tn_attn_fwd_bf16"] * 1e-3) / 1e12
+            out["attn_fwd_tflops_mask_exact"] = tf
+            out["attn_fwd_mfu_mask_exact"] = tf / peak
+        if per.get("tn_attn_bwd_bf16"):
+            tb = 2.5 * attn_fwd_flop_step / (per["tn_attn_bwd_bf16"] * 1e-3) / 1e12
+            out["attn_bwd_tflops_mask_exact_2p5x"] = tb
+            out["attn_bwd_mfu_mask_exact"] = tb / peak
+        gb = lambda bytes_, ms: bytes_ / (ms * 1e-3) / 1e9
+        n_norm = 2 * layers + 1
+        if per.get("tn_rmsnorm_fwd_bf16"):
+            out["hbm_gbps_rmsnorm_fwd"] = gb(n_norm * rows * d * 4, per["tn_rmsnorm_fwd_bf16"])
+        if per.get("tn_rmsnorm_bwd_bf16"):
+            out["hbm_gbps_rmsnorm_bwd"] = gb(n_norm * rows * d * 8, per["tn_rmsnorm_bwd_bf16"])
+        if per.get("tn_swiglu_bwd_bf16"):
+            out["hbm_gbps_swiglu_bwd"] = gb(layers * rows * ffn * 10, per["tn_swiglu_bwd_bf16"])
+        if per.get("tn_pack_ce_fwd_bf16"):
+            out["hbm_gbps_pack_ce_fwd"] = gb(rows * V * 2, per["tn_pack_ce_fwd_bf16"])
+        if per.get("tn_pack_ce_bwd_bf16"):
+            out["hbm_gbps_pack_ce_bwd"] = gb(rows * V * 4, per["tn_pack_ce_bwd_bf16"])
+        out["hbm_peak_gbps"] = peaks.get("hbm")
+        # the reference's own MFU line (touchnet/models/llama/__init__.py:39-54: 6*N_non_embedding + 12*L*H*hd*T per token)
+        H = text["num_attention_heads"]
+        n_non_emb = layers * (2 * d * H * 128 + 2 * d * text["num_key_value_heads"] * 128 + 3 * d * ffn + 2 * d) + d
+        flop_tok = 6 * n_non_emb + 12 * layers * H * 128 * T
+        out["mfu_reference_convention_dense_attention_flops"] = flop_tok * tokens_per_step / (ms_per_step * 1e-3) / 1e12 / peak
+    except Exception as e:                     # the headline line must never depend on these
+        out["derived_columns_error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
 def gemm_traffic():
     """Average DRAM bytes per GEMM launch of the step, from the committed ncu capture (profiles/r01_gemm_traffic.json)."""
     p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
@@ -532,7 +574,9 @@ def main():
                    "attn_fwd_tflop_mask_exact_per_step_rank0": attn_fwd / 1e12, "loss": final_loss,
                    "model_tflop_per_step_rank0": gemm_flops / args.steps / 1e12,
                    "ms_by_entry_point_timed_region": gt.by_class(),
-                   "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30},
+                   "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                   "report_columns_rank0": derived_columns(gt.by_class(), args.steps, ms / args.steps, attn_fwd,
+                                                           meta["nonpad_tokens"], B * T, B, T, n_layers, peaks, _W["text"])},
     }
     if world == 1 and not args.no_cpu_baseline:
         state = cpu_reference_setup()

@@ -112,3 +112,35 @@ def test_oracle_mask_semantics():
     q = torch.randn(1, 2, 7, 8); k = torch.randn(1, 1, 7, 8); v = torch.randn(1, 1, 7, 8)
     o, lse = mo.attention(q, k, v, mo.doc_causal_allow(doc), 8 ** -0.5)
     assert torch.all(o[0, 5:] == 0) and torch.isinf(lse[0, :, 5:]).all()   # FlexAttention: exact zeros
+
+
+def test_pack_loss_oracle_has_the_invariance_the_reference_tests():
+    """ref: tests/touchnet/utils/test_pack_loss.py - the loss of sentences trained as a padded batch (per-sentence token
+    mean, then mean over sentences: calc_batch_dp_loss) equals the loss of the same sentences PACKED into one row and
+    normalised through sentence_lens / num_sentence (calc_pack_sp_loss; touchnet/loss/cross_entropy.py:12-50).  The oracle
+    restatement must have exactly that property (the CUDA loss is then compared with the oracle in tests/test_gpu_loss.py)."""
+    import torch
+    from oracle import model_oracle as mo
+    g = torch.Generator().manual_seed(0)
+    V, lens = 37, [5, 11, 3, 8]
+    L = max(lens)
+    logits_b = torch.randn(len(lens), L, V, generator=g)
+    labels_b = torch.full((len(lens), L), -100, dtype=torch.int64)
+    for i, n in enumerate(lens):
+        labels_b[i, :n] = torch.randint(0, V, (n,), generator=g)
+    # (a) the reference test's padded-batch formula
+    ce = torch.nn.functional.cross_entropy(logits_b.reshape(-1, V), labels_b.reshape(-1), reduction="none", ignore_index=-100)
+    batch_loss = (ce.reshape(len(lens), -1).sum(1) / ((labels_b != -100).sum(1).float() + 1e-12)).mean()
+    # (b) the same sentences packed into one row of length 32 (5 pad positions at the end)
+    T = 32
+    logits_p = torch.randn(1, T, V, generator=g)
+    labels_p = torch.full((1, T), -100, dtype=torch.int64)
+    sl = torch.ones(1, T, dtype=torch.int64)
+    o = 0
+    for i, n in enumerate(lens):
+        logits_p[0, o:o + n] = logits_b[i, :n]
+        labels_p[0, o:o + n] = labels_b[i, :n]
+        sl[0, o:o + n] = n
+        o += n
+    per_sample = mo.pack_loss(logits_p, labels_p, sl, len(lens))
+    assert abs(float(per_sample) - float(batch_loss)) < 1e-6

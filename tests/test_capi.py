@@ -61,3 +61,27 @@ def test_ctypes_signatures_match_the_header_arity():
         assert name in _lib._SIGNATURES, f"{name} is declared in the header but has no ctypes signature"
         assert len(_lib._SIGNATURES[name]) == n, (name, len(_lib._SIGNATURES[name]), n)
     assert set(_lib._SIGNATURES) <= {p[0] for p in protos}, "ctypes signature without a header prototype"
+
+
+def test_argument_errors_of_the_entry_points_added_late_in_round_1():
+    """Argument validation happens before any CUDA call, so it can be exercised without a GPU: non-zero return code +
+    tn_last_error() -> TouchNetB200Error (the reference's convention is Python exceptions)."""
+    import ctypes
+    import pytest
+    from touchnet_b200 import _lib
+    arr = (ctypes.c_void_p * 2)(16, 32)
+    bad_calls = [
+        ("tn_peer_reduce_scatter_f32", (arr, 0, 0, 64, 4, 1.0, 32, None), "n_peers"),
+        ("tn_peer_reduce_scatter_f32", (arr, 2, 3, 64, 4, 1.0, 32, None), "multiple of 4"),
+        ("tn_peer_all_gather", (arr, 2, 24, 64, 32, None), "multiple of 16"),
+        ("tn_set_gemm_group", (0,), "out of range"),
+        ("tn_set_sm_margin", (-1,), "out of range"),
+        ("tn_adamw_f32", (None, None, None, None, None, 4, 1e-3, 0.9, 0.95, 1e-8, 0.1, 0.1, 0.1, None, None), "null"),
+        ("tn_pack_layout_i64", (None, None, None, None, None, None, 0, 1, 8, 0, 1, 2, None, None, None, None, None, None), "null"),
+        ("tn_sumsq_f32", (None, 4, None, None, None), "null"),
+    ]
+    for name, args, needle in bad_calls:
+        with pytest.raises(_lib.TouchNetB200Error, match=needle):
+            _lib.call(name, *args)
+    _lib.call("tn_set_gemm_group", 8)          # valid values are accepted without a device
+    _lib.call("tn_set_sm_margin", 0)

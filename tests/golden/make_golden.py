@@ -9,8 +9,10 @@ What is executed to produce each file
                        on seeded noise/chirp waveforms and on the two real wavs of the reference's own tests
                        (tests/assets/dataset/*.wav, PCM parsed with the stdlib `wave` module).
   frontend_logmel.npz  the torch.stft path of touchnet/data/functions.py:168-189 executed line by line with torch,
-                       with librosa.filters.mel replaced by the restated Slaney bank (librosa is not installed:
-                       that one factor is unpinned and says so).
+                       with librosa.filters.mel (absent here) supplied by an INDEPENDENT third-party implementation of
+                       the same published algorithm: transformers.audio_utils.mel_filter_bank(norm="slaney",
+                       mel_scale="slaney") - the function WhisperFeatureExtractor builds its `mel_filters` from. The
+                       bank itself is stored too (`slaney/<n_mels>`), so the oracle's restatement is pinned against it.
   model_tiny.npz       installed HF LlamaForCausalLM (eager attention, fp32) on the reference's test config
                        tests/assets/config/tiny_llama.json with a dense 4-D document mask, and the reference's own
                        TouchAudioForCausalLM wrapper (per-module import) around the same text config.
@@ -109,9 +111,17 @@ def golden_frontend(functions):
     np.savez_compressed(os.path.join(HERE, "frontend_fbank.npz"), **out)
     print("frontend_fbank.npz", {k: v.shape for k, v in out.items() if k.startswith("fbank/")})
 
-    # log-mel: functions.py:168-189 with the restated Slaney filters
-    from oracle.frontend_oracle import slaney_mel_filters
+    # log-mel: functions.py:168-189; librosa.filters.mel(sr=16000, n_fft=400, n_mels) comes from transformers'
+    # mel_filter_bank (Slaney scale + Slaney norm, fmin 0, fmax sr/2 = librosa's defaults), NOT from our restatement
+    from transformers.audio_utils import mel_filter_bank
+
+    def slaney_mel_filters(sr, n_fft, n_mels):
+        return mel_filter_bank(num_frequency_bins=1 + n_fft // 2, num_mel_filters=n_mels, min_frequency=0.0,
+                               max_frequency=sr / 2.0, sampling_rate=sr, norm="slaney",
+                               mel_scale="slaney").T.astype(np.float32)
     out = {}
+    for n_mels in (80, 128):
+        out[f"slaney/{n_mels}"] = slaney_mel_filters(16000, 400, n_mels)
     for name in ("noise_1s", "chirp", "noise_odd"):
         wav = torch.from_numpy(wavs[name])
         for n_mels in (80, 128):
@@ -267,6 +277,9 @@ def golden_bestrq():
 
 if __name__ == "__main__":
     functions = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "frontend":
+        golden_frontend(functions)
+        sys.exit(0)
     golden_frontend(functions)
     golden_batching()
     golden_bestrq()

@@ -31,7 +31,8 @@ def oracle_cfg(c, audio=0):
                            num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
                            num_key_value_heads=c.num_key_value_heads, head_dim=128, vocab_size=c.vocab_size,
                            rms_norm_eps=c.rms_norm_eps, rope_theta=c.rope_theta, rope_scaling=c.rope_scaling,
-                           attention_bias=c.attention_bias, audio_input_size=audio)
+                           attention_bias=c.attention_bias, audio_input_size=audio,
+                           pad_token_id=getattr(c, "pad_token_id", None))
 
 
 LLAMA3 = {"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,

@@ -51,9 +51,28 @@ def test_logmel_oracle_matches_torch_stft_path(golden_dir):
         np.testing.assert_allclose(out, g[k], atol=2e-4, rtol=0, err_msg=k)
 
 
+def test_slaney_filters_pinned_to_whisper_mel_filter_bank(golden_dir):
+    """The restated librosa.filters.mel equals the bank stored in the fixture, which was produced by
+    transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney") - the function Whisper's feature
+    extractor builds its filters from (an independent implementation of librosa's published algorithm)."""
+    g = np.load(os.path.join(golden_dir, "frontend_logmel.npz"))
+    for n_mels in (80, 128):
+        ref = g[f"slaney/{n_mels}"]
+        w = fo.slaney_mel_filters(16000, 400, n_mels)
+        assert w.shape == ref.shape == (n_mels, 201)
+        np.testing.assert_allclose(w, ref, rtol=0, atol=1e-7)
+    try:        # and live, when transformers is importable on this box (it is not needed for the assertion above)
+        from transformers.audio_utils import mel_filter_bank
+    except Exception:
+        return
+    live = mel_filter_bank(num_frequency_bins=201, num_mel_filters=80, min_frequency=0.0, max_frequency=8000.0,
+                           sampling_rate=16000, norm="slaney", mel_scale="slaney").T
+    np.testing.assert_allclose(fo.slaney_mel_filters(16000, 400, 80), live, rtol=0, atol=1e-7)
+
+
 def test_slaney_filters_have_whisper_properties():
-    """librosa itself is absent (parity unpinned for this factor): check the published properties of whisper's
-    mel_filters - shape, Slaney area normalisation, triangular support, monotone centres."""
+    """Published properties of whisper's mel_filters - shape, Slaney area normalisation, triangular support,
+    monotone centres."""
     for n_mels in (80, 128):
         w = fo.slaney_mel_filters(16000, 400, n_mels)
         assert w.shape == (n_mels, 201) and (w >= 0).all()

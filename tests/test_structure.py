@@ -114,6 +114,10 @@ def test_public_modules_import_without_cuda_and_specs_carry_the_b200_parallelize
         from touchnet.utils.train_spec import get_train_spec          # reference importable: its registry holds the spec
         spec = get_train_spec("llama_b200")
     assert spec.parallelize_fn.__name__ == "parallelize_b200"
+    # the loss / accuracy slots the train loop consumes (ref: touchnet/bin/train.py:447-450) are the CUDA pack-loss, not
+    # the reference's compiled fp32-upcast cross-entropy
+    from touchnet_b200 import loss
+    assert spec.loss_fn is loss.cross_entropy_loss and spec.acc_fn is loss.accuracy
 
 
 def test_parallelize_fn_hands_the_reference_function_a_view_without_tp():

@@ -62,7 +62,8 @@ class _PackCEFn(torch.autograd.Function):
         g = g_loss.reshape(1).float().contiguous()
         _lib.call("tn_pack_ce_bwd_bf16", x.data_ptr(), x.stride(0), lab.data_ptr(), sl.data_ptr(), lse.data_ptr(),
                   g.data_ptr(), float(ctx.inv_ns), x.shape[0], x.shape[1], _st())
-        ctx.logits = None
+        torch.autograd.graph.increment_version(x)   # the kernel overwrote the caller's logits with their gradient: make
+        ctx.logits = None                           # autograd (and accuracy()'s cache key) see the mutation
         return x.view(ctx.shape), None, None, None
 
 

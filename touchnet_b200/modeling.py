@@ -176,7 +176,9 @@ class B200LlamaModel(nn.Module):
         self.config = config
         self.padding_idx = _cfg(config, "pad_token_id")
         self.vocab_size = config.vocab_size
-        self.embed_tokens = nn.Embedding(config.vocab_size, config.hidden_size)
+        # hf: LlamaModel.__init__ modeling_llama.py: nn.Embedding(vocab, hidden, padding_idx=config.pad_token_id) - the pad
+        # row is zero at init and receives no gradient (TouchAudio writes the pad id at every audio-frame position)
+        self.embed_tokens = nn.Embedding(config.vocab_size, config.hidden_size, padding_idx=self.padding_idx)
         self.layers = nn.ModuleList([B200DecoderLayer(config, i) for i in range(config.num_hidden_layers)])
         self.norm = B200RMSNorm(config.hidden_size, _cfg(config, "rms_norm_eps", 1e-6))
         self.rotary_emb = B200RotaryEmbedding(config)
@@ -227,8 +229,9 @@ class _EmbedAddFn(torch.autograd.Function):
     """E = embed_tokens(input_ids) + projected audio features (ref: modeling_touch_audio.py:124-131), NaN flag folded in."""
 
     @staticmethod
-    def forward(ctx, input_ids, embed_w, proj, nan_flag):
+    def forward(ctx, input_ids, embed_w, proj, nan_flag, padding_idx=None):
         B, T = input_ids.shape
+        ctx.padding_idx = padding_idx
         d = embed_w.shape[1]
         ids = input_ids.reshape(-1).contiguous()
         p2 = None if proj is None else proj.reshape(B * T, d)
@@ -244,7 +247,9 @@ class _EmbedAddFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             d_embed = torch.zeros(ctx.embed_shape, dtype=ctx.embed_dtype, device=de.device)
             d_embed.index_add_(0, ids, de.reshape(-1, de.shape[-1]).to(ctx.embed_dtype))
-        return None, d_embed, (de if ctx.has_proj else None), None
+            if ctx.padding_idx is not None and 0 <= ctx.padding_idx < ctx.embed_shape[0]:
+                d_embed[ctx.padding_idx].zero_()          # nn.Embedding(padding_idx=...): no gradient for the pad row
+        return None, d_embed, (de if ctx.has_proj else None), None, None
 
 
 class B200LlamaForCausalLM(nn.Module):
@@ -292,6 +297,9 @@ class B200LlamaForCausalLM(nn.Module):
                     nn.init.zeros_(m.bias)
             elif isinstance(m, nn.Embedding):
                 nn.init.normal_(m.weight, 0.0, std)
+                if m.padding_idx is not None and m.weight.device.type != "meta":
+                    with torch.no_grad():
+                        m.weight[m.padding_idx].zero_()     # hf `_init_weights`: the padding row stays zero
             elif isinstance(m, B200RMSNorm):
                 nn.init.ones_(m.weight)
         rot = self.model.rotary_emb
@@ -312,11 +320,13 @@ class B200LlamaForCausalLM(nn.Module):
             if input_ids is None:
                 raise TouchNetB200Error("either input_ids or inputs_embeds is required")
             if tp_group is None:
-                inputs_embeds = _EmbedAddFn.apply(input_ids, self.model.embed_tokens.weight, None, None)
+                inputs_embeds = _EmbedAddFn.apply(input_ids, self.model.embed_tokens.weight, None, None,
+                                                  self.model.embed_tokens.padding_idx)
             else:
                 from . import tensor_parallel
                 inputs_embeds = tensor_parallel.embed(input_ids, self.model.embed_tokens.weight,
-                                                      tensor_parallel.TPContext(tp_group, input_ids.shape[0]))
+                                                      tensor_parallel.TPContext(tp_group, input_ids.shape[0]),
+                                                      self.model.embed_tokens.padding_idx)
         h = self.model(inputs_embeds, attention_mask, position_ids)
         if tp_group is None:
             logits = ops.linear(h, self.lm_head.weight)
@@ -377,8 +387,10 @@ class B200TouchAudioForCausalLM(nn.Module):
         self.language_model.post_init()
 
     def raise_if_nan(self):
-        """The reference syncs every step to raise ValueError("NaN in data.") (modeling_touch_audio.py:133-134).
-        Here the check is a flag written by the embedding kernel; reading it is the caller's (deferred) sync."""
+        """The reference syncs every forward to raise ValueError("NaN in data.") (modeling_touch_audio.py:133-134).
+        Here the scan is a flag written by the embedding kernel itself (no extra pass over E); reading it is the one
+        host sync, done by `forward` every call by default (`check_nan=True`, the reference's behaviour) or by the
+        caller at a step boundary when `forward(check_nan=False)` is used to keep the step free of syncs."""
         if int(self._nan_flag.item()) != 0:
             self._nan_flag.zero_()
             raise ValueError("NaN in data.")
@@ -387,7 +399,7 @@ class B200TouchAudioForCausalLM(nn.Module):
                 attention_mask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None,
                 past_key_values=None, inputs_embeds: Optional[torch.Tensor] = None, labels=None, use_cache=None,
                 output_attentions=None, output_hidden_states=None, return_dict=None, cache_position=None,
-                logits_to_keep=0, check_nan: bool = False, **kwargs: Any):
+                logits_to_keep=0, check_nan: bool = True, **kwargs: Any):
         assert labels is None  # we calculate loss in train-loop (ref: modeling_touch_audio.py:121)
         ops.begin_forward(self)             # projector, decoder layers, lm_head: casts overlap the GEMMs in front of them
         tp_group = getattr(self, "tp_group", None)
@@ -396,7 +408,8 @@ class B200TouchAudioForCausalLM(nn.Module):
             # runs on this rank's rows only, so its gradient is a partial sum over tp -> all-reduced
             from . import tensor_parallel
             tp = tensor_parallel.TPContext(tp_group, input_ids.shape[0])
-            inputs_embeds = tensor_parallel.embed(input_ids, self.language_model.model.embed_tokens.weight, tp)
+            inputs_embeds = tensor_parallel.embed(input_ids, self.language_model.model.embed_tokens.weight, tp,
+                                                  self.language_model.model.embed_tokens.padding_idx)
             if input_features is not None and input_ids.shape[1] != 1:
                 feats = tp.seq_slice(input_features)
                 feats = feats if feats.dtype == torch.bfloat16 else feats.to(torch.bfloat16)
@@ -410,7 +423,8 @@ class B200TouchAudioForCausalLM(nn.Module):
                 feats = input_features if input_features.dtype == torch.bfloat16 else input_features.to(torch.bfloat16)
                 proj = ops.linear(feats, self.projector.weight)
             # text-only batches: the reference pushes zeros through the bias-free projector (:128-130) = adds 0
-            inputs_embeds = _EmbedAddFn.apply(input_ids, lm.model.embed_tokens.weight, proj, self._nan_flag)
+            inputs_embeds = _EmbedAddFn.apply(input_ids, lm.model.embed_tokens.weight, proj, self._nan_flag,
+                                              lm.model.embed_tokens.padding_idx)
         if check_nan:
             self.raise_if_nan()
         outputs = self.language_model(input_ids=None, attention_mask=attention_mask, position_ids=position_ids,

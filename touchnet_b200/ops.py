@@ -47,6 +47,7 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     if out is None:
         out = torch.empty(src.shape, dtype=BF16, device=src.device)
     _lib.call("tn_cast_f32_bf16", src.data_ptr(), out.data_ptr(), src.numel(), _st())
+    torch.autograd.graph.increment_version(out)   # raw-pointer write: a graph that saved `out` for backward must notice
     return out
 
 

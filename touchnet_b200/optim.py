@@ -35,7 +35,10 @@ def _sumsq(x: torch.Tensor) -> torch.Tensor:
     if _n_partials is None:
         _n_partials = _lib.load().tn_sumsq_num_partials()
     ops._chk(x, "grad", torch.float32)
-    x = x.contiguous()
+    if x.numel() == 0:          # an empty local shard (uneven FSDP2 sharding): contributes 0, every rank stays in step
+        return torch.zeros((), dtype=torch.float32, device=x.device)
+    if not x.is_contiguous() or x.data_ptr() % 16:
+        x = x.contiguous().clone()   # unaligned FSDP2 gradient view: the kernel wants 16-byte vectors (read-only use)
     part = torch.empty(_n_partials, dtype=torch.float32, device=x.device)
     used = ctypes.c_int(0)
     _lib.call("tn_sumsq_f32", x.data_ptr(), x.numel(), part.data_ptr(), ctypes.byref(used), ops._st())
@@ -86,7 +89,13 @@ def clip_grad_norm_(parameters: Union[torch.Tensor, Iterable[torch.Tensor]], max
     else:
         for g in grads:
             gl = _local(g)
-            _lib.call("tn_scale_f32", gl.data_ptr(), gl.numel(), coef.data_ptr(), ops._st())
+            if gl.numel() == 0:
+                continue
+            if gl.is_contiguous() and gl.data_ptr() % 16 == 0:
+                _lib.call("tn_scale_f32", gl.data_ptr(), gl.numel(), coef.data_ptr(), ops._st())
+                torch.autograd.graph.increment_version(gl)      # written through the raw pointer
+            else:                    # unaligned / strided shard view: same arithmetic, plain in-place multiply
+                gl.mul_(coef)
     return total_norm
 
 
@@ -122,6 +131,8 @@ class B200AdamW(torch.optim.Optimizer):
                 st["step"] += 1
                 t = float(st["step"])
                 pl, gl = _local(p), _local(p.grad)
+                if pl.numel() == 0:
+                    continue
                 ml, vl = _local(st["exp_avg"]), _local(st["exp_avg_sq"])
                 if pl.dtype != torch.float32 or gl.dtype != torch.float32:
                     raise _lib.TouchNetB200Error("B200AdamW needs fp32 parameters and gradients (fp32 master weights)")
@@ -138,6 +149,7 @@ class B200AdamW(torch.optim.Optimizer):
                           ops._st())
                 torch.autograd.graph.increment_version(pl)      # the kernel wrote through the raw pointer
                 if pb is not None:
+                    torch.autograd.graph.increment_version(pb)
                     p._tn_bf16 = (p._version, pb, None, ops._CACHE_EPOCH)   # fresh working copy: next forward casts nothing
         self.grad_scale = None
         return loss

@@ -159,13 +159,15 @@ class _VocabParallelEmbed(torch.autograd.Function):
     local lookup (zeros for ids owned by other ranks) -> reduce-scatter along the sequence."""
 
     @staticmethod
-    def forward(ctx, ids, w_local, tp: TPContext):
+    def forward(ctx, ids, w_local, tp: TPContext, padding_idx=None):
         B, T = ids.shape
         vl = w_local.shape[0]
         loc = ids.reshape(-1) - tp.rank * vl
         mine = (loc >= 0) & (loc < vl)
         loc = loc.clamp(0, vl - 1)
         e = w_local.detach()[loc].to(BF16) * mine[:, None].to(BF16)
+        if padding_idx is not None:     # nn.Embedding(padding_idx=...): the pad row receives no gradient
+            mine = mine & (ids.reshape(-1) != padding_idx)
         ctx.save_for_backward(loc, mine)
         ctx.tp, ctx.w_shape, ctx.w_dtype = tp, w_local.shape, w_local.dtype
         return tp.rs(e).view(B, T // tp.size, -1)
@@ -177,14 +179,14 @@ class _VocabParallelEmbed(torch.autograd.Function):
         de_full = tp.ag(de.reshape(-1, de.shape[-1]).contiguous())
         dw = torch.zeros(ctx.w_shape, dtype=ctx.w_dtype, device=de.device)
         dw.index_add_(0, loc, (de_full * mine[:, None].to(de_full.dtype)).to(ctx.w_dtype))
-        return None, dw, None
+        return None, dw, None, None
 
 
-def embed(ids: torch.Tensor, embed_weight: torch.Tensor, tp: TPContext) -> torch.Tensor:
+def embed(ids: torch.Tensor, embed_weight: torch.Tensor, tp: TPContext, padding_idx=None) -> torch.Tensor:
     """[B, T] ids -> [B, T/tp, d] sequence-sharded embeddings."""
     if ids.shape[1] % tp.size != 0:
         raise ops._lib.TouchNetB200Error(f"T={ids.shape[1]} does not split over tp={tp.size}")
-    return _VocabParallelEmbed.apply(ids, local(embed_weight), tp)
+    return _VocabParallelEmbed.apply(ids, local(embed_weight), tp, padding_idx)
 
 
 def lm_head(h_s: torch.Tensor, weight: torch.Tensor, tp: TPContext) -> torch.Tensor:

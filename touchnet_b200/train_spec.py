@@ -5,8 +5,10 @@ Two seams:
 1. Outer plugin API - `TrainSpec` (ref: touchnet/utils/train_spec.py:25-62).  `register()` clones the reference's own
    "llama" / "touch_audio" specs (ref: touchnet/__init__.py:35-117) and swaps `model_cls` for the B200 modules under the
    names "llama_b200" / "touch_audio_b200"; `parallelize_fn` is wrapped (parallelize.py: tensor / context parallelism
-   are applied to the fused block, FSDP2 / AC stay the reference's); every other callable (dataloader, optimizer, loss,
-   flops ...) stays the reference's.  `--training_model_name touch_audio_b200` then selects it (ref: touchnet/bin/train.py:119).
+   are applied to the fused block, FSDP2 / AC stay the reference's); `loss_fn` / `acc_fn` become the CUDA pack-loss
+   cross-entropy and its argmax accuracy (loss.py; same signatures and return values as
+   ref: touchnet/loss/cross_entropy.py:12-50 and touchnet/utils/metrics.py:26-50, consumed at train.py:447-450); every
+   other callable (dataloader, tokenizer, optimizer, lr schedule, flops ...) stays the reference's.  `--training_model_name touch_audio_b200` then selects it (ref: touchnet/bin/train.py:119).
 
 2. Inner operator API - HF's attention-interface registry
    (`ALL_ATTENTION_FUNCTIONS[config._attn_implementation]`, hf: models/llama/modeling_llama.py:272-286;
@@ -24,6 +26,7 @@ from typing import Any, Callable, Optional
 
 import torch
 
+from . import loss as _loss
 from . import modeling, ops, parallelize
 
 _tls = threading.local()
@@ -74,28 +77,33 @@ def register(touchnet_pkg=None) -> list[str]:
     """Register "llama_b200" and "touch_audio_b200".  With the reference importable its registry is used (and its own
     specs cloned); otherwise the specs land in this module's registry with the reference-independent callables."""
     names = []
+    pairs = (("llama", modeling.B200LlamaForCausalLM), ("touch_audio", modeling.B200TouchAudioForCausalLM))
     try:
         if touchnet_pkg is None:
-            import touchnet as touchnet_pkg  # type: ignore
+            import touchnet as touchnet_pkg  # type: ignore  # noqa: F401
         from touchnet.utils.train_spec import get_train_spec, register_train_spec  # type: ignore
-        for base, cls in (("llama", modeling.B200LlamaForCausalLM), ("touch_audio", modeling.B200TouchAudioForCausalLM)):
-            ref_spec = get_train_spec(base)
-            spec = dataclasses.replace(ref_spec, name=base + "_b200", model_cls=cls,
-                                       parallelize_fn=parallelize.make_parallelize_fn(ref_spec.parallelize_fn))
-            try:
-                register_train_spec(spec)
-            except ValueError:
-                pass  # already registered
-            names.append(spec.name)
-        return names
-    except Exception:
-        for base, cls in (("llama", modeling.B200LlamaForCausalLM), ("touch_audio", modeling.B200TouchAudioForCausalLM)):
+    except ImportError:
+        # the reference package is not importable here (SURVEY 9.10): keep the specs in this module's registry.
+        # Only ImportError is tolerated - any other failure of the reference branch is a real integration error.
+        for base, cls in pairs:
             spec = TrainSpec(name=base + "_b200", model_cls=cls, config_cls=None,
                              parallelize_fn=parallelize.make_parallelize_fn(None),
+                             loss_fn=_loss.cross_entropy_loss, acc_fn=_loss.accuracy,
                              get_num_flop_per_token_fn=get_num_flop_per_token, get_num_params_fn=get_num_params)
             _local_specs[spec.name] = spec
             names.append(spec.name)
         return names
+    for base, cls in pairs:
+        ref_spec = get_train_spec(base)
+        spec = dataclasses.replace(ref_spec, name=base + "_b200", model_cls=cls,
+                                   parallelize_fn=parallelize.make_parallelize_fn(ref_spec.parallelize_fn),
+                                   loss_fn=_loss.cross_entropy_loss, acc_fn=_loss.accuracy)
+        try:
+            register_train_spec(spec)
+        except ValueError:
+            pass  # already registered
+        names.append(spec.name)
+    return names
 
 
 def get_train_spec(name: str) -> TrainSpec:

@@ -331,10 +331,27 @@ def cpu_reference_step(state):
     return time.perf_counter() - t0
 
 
+def _cpu_threads() -> int:
+    """Threads the CPU arm uses: the cores this process may run on (cgroup/affinity aware), capped at the physical-core
+    count when it can be read - oversubscribing SMT siblings made the round-1 number swing 4x between boxes."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            n = min(n, phys)
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_reference_setup(seed=2025):
     from oracle import model_oracle as mo
     from touchnet_b200 import batching
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(_cpu_threads())
     tc = text_config(1)
     cfg = mo.OracleConfig(hidden_size=tc.hidden_size, intermediate_size=tc.intermediate_size, num_hidden_layers=1,
                           num_attention_heads=tc.num_attention_heads, num_key_value_heads=tc.num_key_value_heads,
@@ -389,10 +406,23 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "packed_tokens_per_sec", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, args.gpus),
+            "config": reference_config(args),
             "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE_DESC},
             "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def reference_config(args):
+    """The CPU arm's OWN configuration (what it really ran), next to the workload it is extrapolated to."""
+    t = _W["text"]
+    return {"workload": f"CPU sample of {_W['name']}: 1 of 32 decoder layers (d={t['hidden_size']} H={t['num_attention_heads']} "
+                        f"KV={t['num_key_value_heads']} ffn={t['intermediate_size']}), fp32, eager attention with the dense "
+                        f"document mask, one packed row of {CPU_SAMPLE_T} tokens + fbank80 stack{STACK}/stride{STRIDE} of that "
+                        f"row's audio, fwd+bwd; tokens/s extrapolated as {CPU_SAMPLE_T}/(32 x t_sample); embeddings, lm_head "
+                        f"and loss not charged",
+            "global_batch": 1, "seq_len": CPU_SAMPLE_T, "layers_measured": 1, "layers_extrapolated_to": 32,
+            "parallelism": f"host CPU, {_cpu_threads()} threads (torch intra-op), no GPU",
+            "extrapolated_to": workload_config(args, args.gpus)["workload"]}
 
 
 def workload_config(args, n):

@@ -132,11 +132,75 @@ def test_touch_audio_forward_backward_parity():
     for name, p in model.named_parameters():
         e = rel_err(p.grad.float(), params32[name].grad)
         assert e < 3e-2, (name, e)
-    # NaN in the features -> ValueError("NaN in data."), as ref modeling_touch_audio.py:133-134
+    # NaN in the features -> ValueError("NaN in data.") raised by forward itself, as ref modeling_touch_audio.py:133-134
     feats[0, 3, 5] = float("nan")
-    model(input_ids=ids, input_features=feats, attention_mask=doc, position_ids=pos)
+    with pytest.raises(ValueError, match="NaN in data"):
+        model(input_ids=ids, input_features=feats, attention_mask=doc, position_ids=pos)
+    model(input_ids=ids, input_features=feats, attention_mask=doc, position_ids=pos, check_nan=False)   # deferred form
     with pytest.raises(ValueError, match="NaN in data"):
         model.raise_if_nan()
+    feats[0, 3, 5] = 0.0
+    model(input_ids=ids, input_features=feats, attention_mask=doc, position_ids=pos)    # the flag was cleared
+
+
+@pytest.mark.parametrize("mode", ["full", "selective_op"])
+def test_activation_checkpointing_wrappers_are_exact(mode):
+    """SURVEY 2 row 6 (compatibility constraint): the reference wraps every decoder block in `checkpoint_wrapper`
+    (full: touchnet/models/helper_func.py:48-49; op-selective SAC: :58-85, run.sh:158 uses full).  The fused block must
+    recompute to the same bits: loss and every gradient equal the un-checkpointed run exactly (deterministic kernels;
+    the in-place RoPE / residual epilogues live inside one autograd node, so recomputation sees pristine inputs)."""
+    from collections import defaultdict
+    from torch.distributed.algorithms._checkpoint.checkpoint_wrapper import checkpoint_wrapper
+    dev = require_cuda()
+    cfg = small_cfg(L=3, rope_scaling=LLAMA3)
+    B, T = 2, 384
+    doc, pos = packed_doc_ids(B, T, [[100, 200, 50], [384]], dev)
+    torch.manual_seed(11)
+    ids = torch.randint(1, cfg.vocab_size, (B, T), device=dev)
+    labels = torch.randint(0, cfg.vocab_size, (B, T), device=dev)
+    labels[doc == 0] = -100
+
+    def build():
+        torch.manual_seed(2025)
+        m = modeling.B200LlamaForCausalLM(cfg).to(dev)
+        m.post_init()
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.dim() == 2:
+                    p.normal_(0, 0.05)
+        return m
+
+    def run(m):
+        logits = m(input_ids=ids, attention_mask=doc, position_ids=pos).logits
+        loss = torch.nn.functional.cross_entropy(logits.float().view(-1, cfg.vocab_size), labels.view(-1), ignore_index=-100)
+        loss.backward()
+        return loss.detach(), {n.replace("._checkpoint_wrapped_module", ""): p.grad.clone() for n, p in m.named_parameters()}
+
+    loss0, g0 = run(build())
+    m = build()
+    layers = m.model.layers
+    for name, block in list(layers.named_children()):
+        if mode == "full":
+            wrapped = checkpoint_wrapper(block, preserve_rng_state=False)
+        else:
+            from torch.utils.checkpoint import CheckpointPolicy, create_selective_checkpoint_contexts
+
+            def ctx_fn():
+                meta = defaultdict(int)
+
+                def policy(ctx, func, *args, **kwargs):        # the reference's policy: save every 2nd aten.mm
+                    if func == torch.ops.aten.mm.default:
+                        meta["mm"] += 1
+                        return CheckpointPolicy.MUST_SAVE if meta["mm"] % 2 else CheckpointPolicy.PREFER_RECOMPUTE
+                    return CheckpointPolicy.PREFER_RECOMPUTE
+                return create_selective_checkpoint_contexts(policy)
+            wrapped = checkpoint_wrapper(block, context_fn=ctx_fn, preserve_rng_state=False)
+        layers.register_module(name, wrapped)
+    loss1, g1 = run(m)
+    assert torch.equal(loss0, loss1)
+    assert g0.keys() == g1.keys()
+    for n in g0:
+        assert torch.equal(g0[n], g1[n]), n
 
 
 def test_plain_causal_defaults_and_text_only_batches():

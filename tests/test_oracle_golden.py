@@ -163,3 +163,31 @@ def test_pack_loss_oracle_has_the_invariance_the_reference_tests():
         o += n
     per_sample = mo.pack_loss(logits_p, labels_p, sl, len(lens))
     assert abs(float(per_sample) - float(batch_loss)) < 1e-6
+
+
+def test_chunked_attention_oracle_equals_dense_oracle_and_its_autograd():
+    """oracle.attention_chunked (what the full-size GPU parity tests compare against) is the same arithmetic as the dense
+    `attention` pinned above, and its analytic backward equals autograd of the dense form (fp32, CPU, small case incl.
+    padding, GQA and a query-chunk boundary inside a document)."""
+    import math
+    import torch
+    from tests.gpu_util import packed_doc_ids
+    torch.manual_seed(0)
+    B, T, H, KV, hd = 2, 192, 4, 2, 16
+    doc, _ = packed_doc_ids(B, T, [[50, 100, 30], [192]])
+    q = torch.randn(B * T, H * hd); k = torch.randn(B * T, KV * hd); v = torch.randn(B * T, KV * hd)
+    do = torch.randn(B * T, H * hd)
+    sc = 1 / math.sqrt(hd)
+    o, lse, dq, dk, dv = mo.attention_chunked(q, k, v, doc, H, KV, sc, do, q_chunk=64)
+    qf = q.view(B, T, H, hd).transpose(1, 2).clone().requires_grad_(True)
+    kf = k.view(B, T, KV, hd).transpose(1, 2).clone().requires_grad_(True)
+    vf = v.view(B, T, KV, hd).transpose(1, 2).clone().requires_grad_(True)
+    o_ref, lse_ref = mo.attention(qf, kf, vf, mo.doc_causal_allow(doc), sc)
+    o_ref.backward(do.view(B, T, H, hd))
+    fin = torch.isfinite(lse_ref)
+    assert torch.equal(torch.isinf(lse), ~fin)
+    assert float((lse - lse_ref)[fin].abs().max()) < 1e-5
+    assert float((o - o_ref.reshape(B * T, -1)).abs().max()) < 1e-5
+    tok = lambda g: g.transpose(1, 2).reshape(B * T, -1)
+    for a, r in ((dq, tok(qf.grad)), (dk, tok(kf.grad)), (dv, tok(vf.grad))):
+        assert float((a - r).abs().max()) < 2e-5

@@ -183,6 +183,11 @@ int tn_pack_ce_fwd_bf16(const void* logits, int64_t ld, const int64_t* labels, f
                         int64_t M, int V, tn_stream_t stream);
 int tn_pack_ce_bwd_bf16(void* logits, int64_t ld, const int64_t* labels, const int64_t* sentence_lens, const float* lse,
                         const float* grad_scalar, float scale, int64_t M, int V, tn_stream_t stream);
+/* fwd and bwd (upstream gradient 1) of the above in ONE launch over a chunk of rows: the building block of the fused
+ * lm_head + loss (touchnet_b200/loss.py::FusedLinearCEFn - the reference's best path is Liger's fused-linear-cross-entropy,
+ * touchnet/bin/train.py:443-445, which never materialises [B,T,V] logits either).  IN PLACE like the bwd entry point. */
+int tn_pack_ce_fused_bf16(void* logits, int64_t ld, const int64_t* labels, const int64_t* sentence_lens, float* lse,
+                          float* ce, int32_t* argmax, float scale, int64_t M, int V, tn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * BEST-RQ tokenizer: labels of audio pre-training.  touchnet/tokenizer/tokenizer.py:289-299.
@@ -206,6 +211,7 @@ int tn_bestrq_tokenize_f32(const float* feats, int64_t ld, const float* proj, co
 int tn_sumsq_num_partials(void);
 int tn_sumsq_f32(const float* x, int64_t n, float* partials, int* n_partials_used, tn_stream_t stream);
 int tn_scale_f32(float* x, int64_t n, const float* scale, tn_stream_t stream);
+int tn_scale_bf16(void* x, int64_t n, const float* scale, tn_stream_t stream);   /* same, bf16 data (no-op when scale is 1) */
 int tn_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, int64_t n,
                  float lr, float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
                  float bias_correction2_sqrt, const float* grad_scale, tn_stream_t stream);

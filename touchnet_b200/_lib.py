@@ -52,6 +52,8 @@ _SIGNATURES = {
     "tn_sumsq_num_partials": [],
     "tn_sumsq_f32": [_vp, _i64, _vp, _vp, _vp],
     "tn_scale_f32": [_vp, _i64, _vp, _vp],
+    "tn_scale_bf16": [_vp, _i64, _vp, _vp],
+    "tn_pack_ce_fused_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f, _i64, _i, _vp],
     "tn_adamw_f32": [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _f, _vp, _vp],
 }
 _RESTYPES = {"tn_last_error": c_char_p, "tn_attn_meta_ints": c_int64}

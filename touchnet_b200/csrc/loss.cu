@@ -118,6 +118,90 @@ __global__ void __launch_bounds__(CE_THREADS) pack_ce_bwd_kernel(bf16* __restric
   }
 }
 
+// Fused form for the chunked lm_head + loss (touchnet_b200/loss.py::FusedLinearCEFn): one CTA per row, pass 1 = the forward
+// reduction above, pass 2 re-reads the row (256 KB at V = 128 k: it is still in L2) and overwrites it with
+// dlogits = (softmax - onehot) * scale / sentence_len, i.e. the gradient for an upstream gradient of 1.
+__global__ void __launch_bounds__(CE_THREADS) pack_ce_fused_kernel(bf16* __restrict__ logits, int64_t ld,
+                                                                   const int64_t* __restrict__ labels,
+                                                                   const int64_t* __restrict__ sentence_lens,
+                                                                   float* __restrict__ lse_out, float* __restrict__ ce_out,
+                                                                   int32_t* __restrict__ argmax_out, float scale, int64_t M,
+                                                                   int V) {
+  __shared__ MaxSum red[CE_THREADS / 32];
+  __shared__ float s_lse;
+  const int64_t row = blockIdx.x;
+  bf16* x = logits + row * ld;
+  const int nvec = V >> 3;
+  MaxSum acc{-INFINITY, 0.f, 0x7fffffff};
+  for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
+    const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] = bf16lo(w[j]); f[2 * j + 1] = bf16hi(w[j]); }
+    float vm = f[0];
+    int vi = 0;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) if (f[j] > vm) { vm = f[j]; vi = j; }
+    if (vm > acc.m) {
+      acc.s = (acc.m == -INFINITY) ? 0.f : acc.s * __expf(acc.m - vm);
+      acc.m = vm;
+      acc.idx = i * 8 + vi;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.s += __expf(f[j] - acc.m);
+  }
+  for (int c = nvec * 8 + threadIdx.x; c < V; c += CE_THREADS) {
+    const float f = __bfloat162float(x[c]);
+    if (f > acc.m) { acc.s = (acc.m == -INFINITY) ? 0.f : acc.s * __expf(acc.m - f); acc.m = f; acc.idx = c; }
+    acc.s += __expf(f - acc.m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MaxSum other;
+    other.m = __shfl_xor_sync(0xffffffffu, acc.m, o);
+    other.s = __shfl_xor_sync(0xffffffffu, acc.s, o);
+    other.idx = __shfl_xor_sync(0xffffffffu, acc.idx, o);
+    acc = ms_merge(acc, other);
+  }
+  if (lane_id() == 0) red[warp_id()] = acc;
+  __syncthreads();
+  const int64_t lab = labels[row];
+  const bool valid = lab >= 0 && lab < V;
+  if (threadIdx.x == 0) {
+    MaxSum t = red[0];
+    for (int w = 1; w < CE_THREADS / 32; ++w) t = ms_merge(t, red[w]);
+    const float lse = t.m + logf(t.s);
+    s_lse = lse;
+    lse_out[row] = lse;
+    ce_out[row] = valid ? lse - __bfloat162float(x[lab]) : 0.f;
+    if (argmax_out) argmax_out[row] = t.idx;
+  }
+  __syncthreads();
+  const float lse = s_lse;
+  const float w = valid ? scale / float(sentence_lens ? sentence_lens[row] : 1) : 0.f;
+  for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
+    uint4 v = reinterpret_cast<const uint4*>(x)[i];
+    uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float p0 = valid ? __expf(bf16lo(ws[j]) - lse) * w : 0.f;
+      float p1 = valid ? __expf(bf16hi(ws[j]) - lse) * w : 0.f;
+      const int c = i * 8 + 2 * j;
+      if (c == lab) p0 -= w;
+      if (c + 1 == lab) p1 -= w;
+      o[j] = pack_bf16x2(p0, p1);
+    }
+    reinterpret_cast<uint4*>(x)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  for (int c = nvec * 8 + threadIdx.x; c < V; c += CE_THREADS) {
+    float p = valid ? __expf(__bfloat162float(x[c]) - lse) * w : 0.f;
+    if (c == lab) p -= w;
+    x[c] = __float2bfloat16_rn(p);
+  }
+}
+
 }  // namespace tn
 
 using namespace tn;
@@ -144,6 +228,20 @@ extern "C" int tn_pack_ce_bwd_bf16(void* logits, int64_t ld, const int64_t* labe
   if (M == 0) return TN_OK;
   pack_ce_bwd_kernel<<<unsigned(M), CE_THREADS, 0, stream>>>(static_cast<bf16*>(logits), ld, labels, sentence_lens, lse,
                                                              grad_scalar, scale, M, V);
+  TN_CHECK_CUDA(cudaGetLastError());
+  return TN_OK;
+}
+
+extern "C" int tn_pack_ce_fused_bf16(void* logits, int64_t ld, const int64_t* labels, const int64_t* sentence_lens,
+                                     float* lse, float* ce, int32_t* argmax, float scale, int64_t M, int V,
+                                     tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(logits && labels && lse && ce, "tn_pack_ce_fused_bf16: null pointer");
+  TN_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0, "tn_pack_ce_fused_bf16: logits rows must be 16 B aligned");
+  if (M == 0) return TN_OK;
+  pack_ce_fused_kernel<<<unsigned(M), CE_THREADS, 0, stream>>>(static_cast<bf16*>(logits), ld, labels, sentence_lens, lse, ce,
+                                                               argmax, scale, M, V);
   TN_CHECK_CUDA(cudaGetLastError());
   return TN_OK;
 }

@@ -106,6 +106,23 @@ __global__ void __launch_bounds__(OPT_THREADS) scale_kernel(float* __restrict__ 
     for (int64_t i = nvec * 4 + threadIdx.x; i < n; i += OPT_THREADS) x[i] *= f;
 }
 
+__global__ void __launch_bounds__(OPT_THREADS) scale_bf16_kernel(uint4* __restrict__ x, int64_t n, const float* __restrict__ s) {
+  const float f = *s;
+  if (f == 1.f) return;                       // the usual upstream gradient of a loss: nothing to do, nothing read
+  const int64_t nvec = n >> 3;
+  for (int64_t i = int64_t(blockIdx.x) * OPT_THREADS + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * OPT_THREADS) {
+    uint4 v = x[i];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = pack_bf16x2(bf16lo(w[j]) * f, bf16hi(w[j]) * f);
+    x[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (blockIdx.x == 0) {
+    bf16* t = reinterpret_cast<bf16*>(x);
+    for (int64_t i = nvec * 8 + threadIdx.x; i < n; i += OPT_THREADS) t[i] = __float2bfloat16_rn(__bfloat162float(t[i]) * f);
+  }
+}
+
 static unsigned grid_for(int64_t n, int max_blocks) {
   int64_t b = (n / 4 + OPT_THREADS - 1) / OPT_THREADS;
   if (b < 1) b = 1;
@@ -159,6 +176,17 @@ extern "C" int tn_scale_f32(float* x, int64_t n, const float* scale, tn_stream_t
   TN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, "tn_scale_f32: x must be 16-byte aligned");
   if (n == 0) return TN_OK;
   scale_kernel<<<grid_for(n, sm_count() * 8), OPT_THREADS, 0, stream>>>(x, n, scale);
+  TN_CHECK_CUDA(cudaGetLastError());
+  return TN_OK;
+}
+
+extern "C" int tn_scale_bf16(void* x, int64_t n, const float* scale, tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(x && scale, "tn_scale_bf16: null pointer");
+  TN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15u) == 0, "tn_scale_bf16: x must be 16-byte aligned");
+  if (n == 0) return TN_OK;
+  scale_bf16_kernel<<<grid_for(n / 2, sm_count() * 8), OPT_THREADS, 0, stream>>>(static_cast<uint4*>(x), n, scale);
   TN_CHECK_CUDA(cudaGetLastError());
   return TN_OK;
 }

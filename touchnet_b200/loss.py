@@ -9,6 +9,14 @@
 The CUDA kernels (csrc/loss.cu) stream the bf16 logits once forward (online logsumexp + argmax) and once backward,
 overwriting them in place with the logit gradient; no fp32 copy of the [B,T,V] tensor is ever made.  In-place is safe in
 the reference's loop order: loss_fn and acc_fn run, `del pred`, then backward (ref: touchnet/bin/train.py:447-455).
+
+Fused lm_head + loss (SURVEY 8(f) rank 1 as written: "no [B,T,V] logits"): when the model runs with
+`fused_linear_ce` (modeling.py) its `pred.logits` is a `LazyLogits` handle (final hidden states + lm_head weight) and
+`cross_entropy_loss` runs `FusedLinearCEFn`: per chunk of `FUSED_CE_CHUNK` token rows - lm_head GEMM into ONE reusable
+[chunk, V] bf16 buffer, `tn_pack_ce_fused_bf16` (loss statistics + argmax + in-place logit gradient), dgrad GEMM into
+dh[chunk], wgrad GEMM accumulating into dW - the way the incumbent's best path does it (Liger fused-linear-cross-entropy,
+ref: touchnet/bin/train.py:443-445).  The [B,T,V] tensor never exists; backward only scales dh / dW by the upstream
+gradient (a no-op kernel when that is 1).
 """
 from __future__ import annotations
 
@@ -67,14 +75,117 @@ class _PackCEFn(torch.autograd.Function):
         return x.view(ctx.shape), None, None, None
 
 
-def cross_entropy_loss(pred: torch.Tensor, labels: torch.Tensor, sentence_lens: torch.Tensor, num_sentence: int,
+FUSED_CE_CHUNK = 2048     # token rows per chunk: the [chunk, V] buffer is 0.5 GB at V = 128 k instead of 2.1 GB for T = 8192,
+                          # and a 2048-row wgrad GEMM (1.5 ms) still hides the read-modify-write of the fp32 dW (0.65 ms)
+
+
+class LazyLogits:
+    """`pred.logits` of a model running with the fused lm_head + loss: NOT a tensor - the final hidden states and the
+    lm_head weight, from which `cross_entropy_loss` / `accuracy` compute what the reference computes from logits.
+    `materialize()` gives the real (differentiable) [B,T,V] tensor for any other consumer."""
+
+    def __init__(self, hidden: torch.Tensor, weight: torch.Tensor):
+        self.hidden, self.weight = hidden, weight
+        self.shape = torch.Size((*hidden.shape[:-1], weight.shape[0]))
+        self.dtype, self.device = torch.bfloat16, hidden.device
+        self._stats = None          # (ce [M], argmax [M]) of the last fused pass
+
+    def materialize(self) -> torch.Tensor:
+        from . import ops
+        return ops.linear(self.hidden, self.weight)
+
+    def dim(self) -> int:
+        return len(self.shape)
+
+    def size(self, i=None):
+        return self.shape if i is None else self.shape[i]
+
+    def __repr__(self):
+        return f"LazyLogits(shape={tuple(self.shape)}, fused lm_head + loss; .materialize() for the tensor)"
+
+
+class FusedLinearCEFn(torch.autograd.Function):
+    """loss_per_sample(h, W) of ref: touchnet/loss/cross_entropy.py:12-50 with logits = h . W^T never materialised.
+    Gradients for an upstream gradient of 1 are produced during forward, chunk by chunk; backward scales them."""
+
+    @staticmethod
+    def forward(ctx, h, w, wb, labels, sentence_lens, inv_num_sentence, chunk):
+        from . import ops
+        d = h.shape[-1]
+        h2 = ops._rows2d(h)
+        if h2.dtype != torch.bfloat16:
+            h2 = h2.to(torch.bfloat16)
+        M, V = h2.shape[0], wb.shape[0]
+        dev = h2.device
+        lab = labels.reshape(-1).contiguous()
+        sl = sentence_lens.reshape(-1).contiguous()
+        assert lab.numel() == M and sl.numel() == M, "labels / sentence_lens must cover every token row"
+        lse = torch.empty(M, dtype=torch.float32, device=dev)
+        ce = torch.empty(M, dtype=torch.float32, device=dev)
+        am = torch.empty(M, dtype=torch.int32, device=dev)
+        need_dh, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        f32 = w.dtype == torch.float32
+        dh = torch.empty((M, d), dtype=torch.bfloat16, device=dev) if need_dh else None
+        dw = torch.empty((V, d), dtype=w.dtype, device=dev) if need_dw else None
+        chunk = max(256, int(chunk))
+        ldv = (V + 7) // 8 * 8                                    # 16-byte aligned rows for any vocabulary size
+        buf = torch.empty((min(chunk, M), ldv), dtype=torch.bfloat16, device=dev)
+        for r0 in range(0, M, chunk):
+            r1 = min(M, r0 + chunk)
+            n = r1 - r0
+            x = buf[:n, :V]
+            ops.gemm(h2[r0:r1], wb, out=x)                                       # logits of this chunk
+            _lib.call("tn_pack_ce_fused_bf16", x.data_ptr(), x.stride(0), lab[r0:r1].data_ptr(), sl[r0:r1].data_ptr(),
+                      lse[r0:r1].data_ptr(), ce[r0:r1].data_ptr(), am[r0:r1].data_ptr(), float(inv_num_sentence), n, V,
+                      _st())                                                    # x now holds dlogits (upstream grad 1)
+            if need_dh:
+                ops.gemm(x, wb, b_mn=True, out=dh[r0:r1])                        # dh = dlogits . W
+            if need_dw:                                                         # dW (+)= dlogits^T . h
+                ops.gemm(x, h2[r0:r1], a_mn=True, b_mn=True, out_f32=f32, residual=dw if r0 > 0 else None, out=dw)
+        ctx.save_for_backward(dh, dw)
+        ctx.h_shape, ctx.h_dtype = h.shape, h.dtype
+        ctx.mark_non_differentiable(ce, am)
+        loss_per_sample = (ce / sl.float()).sum() * inv_num_sentence
+        return loss_per_sample, ce, am
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_ce, _g_am):
+        dh, dw = ctx.saved_tensors
+        g = g_loss.reshape(1).float().contiguous()
+        if dh is not None:
+            _lib.call("tn_scale_bf16", dh.data_ptr(), dh.numel(), g.data_ptr(), _st())     # no-op kernel when g == 1
+            torch.autograd.graph.increment_version(dh)
+            dh = dh.view(ctx.h_shape).to(ctx.h_dtype)
+        if dw is not None:
+            name = "tn_scale_f32" if dw.dtype == torch.float32 else "tn_scale_bf16"
+            _lib.call(name, dw.data_ptr(), dw.numel(), g.data_ptr(), _st())
+            torch.autograd.graph.increment_version(dw)
+        return dh, dw, None, None, None, None, None
+
+
+def fused_linear_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor,
+                               sentence_lens: torch.Tensor, inv_num_sentence: float, chunk: int = 0):
+    """(loss_per_sample, ce [M], argmax [M]) for logits = hidden . weight^T without materialising them."""
+    from . import ops
+    if not hidden.is_cuda:
+        raise _lib.TouchNetB200Error("fused lm_head + loss needs CUDA tensors (no CPU path)")
+    return FusedLinearCEFn.apply(hidden, weight, ops.bf16_weight(weight), labels, sentence_lens, float(inv_num_sentence),
+                                 chunk or FUSED_CE_CHUNK)
+
+
+def cross_entropy_loss(pred, labels: torch.Tensor, sentence_lens: torch.Tensor, num_sentence: int,
                        ignore_index: int = -100):
-    """Same contract as ref: touchnet/loss/cross_entropy.py:12-50.  Returns (loss_per_sample, loss_per_token)."""
+    """Same contract as ref: touchnet/loss/cross_entropy.py:12-50.  Returns (loss_per_sample, loss_per_token).
+    `pred` is the model's `pred.logits`: a bf16 [B,T,V] tensor, or a LazyLogits handle (fused lm_head + loss)."""
     assert ignore_index < 0, "labels outside [0, V) are ignored (the reference uses -100)"
-    B = pred.shape[0]
     global _LAST_ARGMAX
-    loss_per_sample, ce, am = _PackCEFn.apply(pred, labels, sentence_lens, 1.0 / max(int(num_sentence), 1))
-    _LAST_ARGMAX = (weakref.ref(pred), pred._version, am)
+    if isinstance(pred, LazyLogits):
+        loss_per_sample, ce, am = fused_linear_cross_entropy(pred.hidden, pred.weight, labels, sentence_lens,
+                                                             1.0 / max(int(num_sentence), 1))
+        pred._stats = (ce, am)
+    else:
+        loss_per_sample, ce, am = _PackCEFn.apply(pred, labels, sentence_lens, 1.0 / max(int(num_sentence), 1))
+        _LAST_ARGMAX = (weakref.ref(pred), pred._version, am)
     with torch.no_grad():
         num_tokens = (labels != ignore_index).sum()
         tot = ce.sum()
@@ -85,6 +196,18 @@ def cross_entropy_loss(pred: torch.Tensor, labels: torch.Tensor, sentence_lens: 
 def accuracy(pred: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
     """Same contract as ref: touchnet/utils/metrics.py:26-50; reuses the argmax the loss kernel already produced."""
     V = pred.shape[-1]
+    if isinstance(pred, LazyLogits):
+        if pred._stats is None:        # accuracy asked before / without the loss: one statistics-only fused pass
+            with torch.no_grad():
+                ones = torch.ones(labels.numel(), dtype=torch.int64, device=labels.device)
+                _, ce, am = fused_linear_cross_entropy(pred.hidden.detach(), pred.weight.detach(), labels, ones, 1.0)
+            pred._stats = (ce, am)
+        am = pred._stats[1]
+        lab = labels.reshape(-1)
+        mask = lab != ignore_index
+        num = ((am.long() == lab) & mask).sum()
+        den = mask.sum()
+        return torch.where(den > 0, num / den.clamp(min=1), torch.zeros_like(num, dtype=torch.float32)).detach()
     x = pred.view(-1, V)
     ent = _LAST_ARGMAX
     if ent is not None and ent[0]() is pred and ent[1] == pred._version and ent[2].numel() == x.shape[0]:

@@ -252,9 +252,36 @@ class _EmbedAddFn(torch.autograd.Function):
         return None, d_embed, (de if ctx.has_proj else None), None, None
 
 
+def _root_reshards_after_forward(module: nn.Module) -> bool:
+    """True when `module` is an FSDP2 root whose parameter group frees its unsharded parameters when forward returns (the
+    reference's default policy, ref: touchnet/models/helper_func.py:196-202): lm_head.weight must then be consumed INSIDE
+    forward.  Unknown FSDP internals count as "reshards" (the safe answer)."""
+    try:
+        from torch.distributed.fsdp import FSDPModule
+    except ImportError:
+        return False
+    if not isinstance(module, FSDPModule):
+        return False
+    try:
+        grp = module._get_fsdp_state()._fsdp_param_group
+        if grp is None:
+            return False
+        info = getattr(grp, "post_forward_mesh_info", None)
+        flag = getattr(grp, "_reshard_after_forward", None)
+        if flag is not None:
+            return bool(flag)
+        return info is not None
+    except Exception:
+        return True
+
+
 class B200LlamaForCausalLM(nn.Module):
     base_model_prefix = "model"
     _tied_weights_keys = ["lm_head.weight"]
+    # fused lm_head + loss (loss.py::FusedLinearCEFn): in training mode `pred.logits` becomes a loss.LazyLogits handle that
+    # loss.cross_entropy_loss / loss.accuracy consume without ever materialising [B,T,V].  The "*_b200" TrainSpecs switch it
+    # on (train_spec.register: their loss_fn / acc_fn are exactly those two functions); direct users get real logits.
+    fused_linear_ce = False
 
     def __init__(self, config):
         super().__init__()
@@ -328,8 +355,23 @@ class B200LlamaForCausalLM(nn.Module):
                                                       tensor_parallel.TPContext(tp_group, input_ids.shape[0]),
                                                       self.model.embed_tokens.padding_idx)
         h = self.model(inputs_embeds, attention_mask, position_ids)
+        shift_labels = kwargs.get("shift_labels")
+        if shift_labels is not None and tp_group is None and getattr(self.model, "cp_group", None) is None:
+            # the reference's Liger route (ref: touchnet/bin/train.py:437-445: `shift_labels` stays in the batch and
+            # `pred.loss` is used as is): token-mean cross-entropy of the pre-shifted labels, lm_head fused with the loss
+            from . import loss as _loss
+            ones = torch.ones(shift_labels.numel(), dtype=torch.int64, device=shift_labels.device)
+            tot, _, _ = _loss.fused_linear_cross_entropy(h, self.lm_head.weight, shift_labels, ones, 1.0)
+            n_valid = ((shift_labels >= 0) & (shift_labels < self.vocab_size)).sum().clamp(min=1)
+            return CausalLMOutputWithPast(loss=tot / n_valid, logits=None)
         if tp_group is None:
-            logits = ops.linear(h, self.lm_head.weight)
+            fused = (self.fused_linear_ce and self.training and torch.is_grad_enabled()
+                     and not _root_reshards_after_forward(getattr(self, "_tn_fsdp_root", self)))
+            if fused:
+                from . import loss as _loss
+                logits = _loss.LazyLogits(h, self.lm_head.weight)
+            else:
+                logits = ops.linear(h, self.lm_head.weight)
         else:       # h is the sequence shard; logits come back replicated [B, T, V]
             from . import tensor_parallel
             logits = tensor_parallel.lm_head(h, self.lm_head.weight, tensor_parallel.TPContext(tp_group, h.shape[0]))
@@ -354,6 +396,16 @@ class B200TouchAudioForCausalLM(nn.Module):
         self.pad_token_id = pad if pad is not None else -1
         self._padding_side = "left"
         self.register_buffer("_nan_flag", torch.zeros(1, dtype=torch.int32), persistent=False)
+        # lm_head.weight belongs to the FSDP2 ROOT group when this wrapper is the root: the inner model asks it
+        object.__setattr__(self.language_model, "_tn_fsdp_root", self)
+
+    @property
+    def fused_linear_ce(self) -> bool:
+        return self.language_model.fused_linear_ce
+
+    @fused_linear_ce.setter
+    def fused_linear_ce(self, v: bool):
+        self.language_model.fused_linear_ce = bool(v)
 
     @property
     def model(self):  # the reference's llama post_init / get_num_params reach `model.model.*`
@@ -428,7 +480,7 @@ class B200TouchAudioForCausalLM(nn.Module):
         if check_nan:
             self.raise_if_nan()
         outputs = self.language_model(input_ids=None, attention_mask=attention_mask, position_ids=position_ids,
-                                      inputs_embeds=inputs_embeds)
+                                      inputs_embeds=inputs_embeds, **kwargs)
         outputs.attention_mask = attention_mask
         return outputs
 

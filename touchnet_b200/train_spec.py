@@ -56,6 +56,20 @@ class TrainSpec:
 _local_specs: dict[str, TrainSpec] = {}
 
 
+class B200LlamaForCausalLMFused(modeling.B200LlamaForCausalLM):
+    """model_cls of the "llama_b200" spec: the fused lm_head + loss is on (the spec's loss_fn / acc_fn consume the
+    LazyLogits handle; ref contract: touchnet/bin/train.py:439-450)."""
+    fused_linear_ce = True
+
+
+class B200TouchAudioForCausalLMFused(modeling.B200TouchAudioForCausalLM):
+    """model_cls of the "touch_audio_b200" spec (see B200LlamaForCausalLMFused)."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.language_model.fused_linear_ce = True
+
+
 def get_num_flop_per_token(num_params: int, model_config, seq_len: int) -> int:
     """ref: touchnet/models/llama/__init__.py:39-54 (dense-attention convention, no recompute credit)."""
     l, h = model_config.num_hidden_layers, model_config.num_attention_heads
@@ -77,7 +91,7 @@ def register(touchnet_pkg=None) -> list[str]:
     """Register "llama_b200" and "touch_audio_b200".  With the reference importable its registry is used (and its own
     specs cloned); otherwise the specs land in this module's registry with the reference-independent callables."""
     names = []
-    pairs = (("llama", modeling.B200LlamaForCausalLM), ("touch_audio", modeling.B200TouchAudioForCausalLM))
+    pairs = (("llama", B200LlamaForCausalLMFused), ("touch_audio", B200TouchAudioForCausalLMFused))
     try:
         if touchnet_pkg is None:
             import touchnet as touchnet_pkg  # type: ignore  # noqa: F401

@@ -516,6 +516,8 @@ def main():
                 layer.set_modules_to_forward_prefetch(list(layers[i + 1:i + 1 + depth]))
                 layer.set_modules_to_backward_prefetch(list(reversed(layers[max(0, i - depth):i])))
     model.train()
+    # fused lm_head + pack-loss (no [B,T,V] logits): what the "*_b200" TrainSpecs run; TN_FUSED_CE=0 for the A/B
+    model.fused_linear_ce = os.environ.get("TN_FUSED_CE", "1") != "0" and tp == 1
 
     host, meta = make_host_batch(dist_util_seed(2025, rank // (tp * cp)), B, T, cfg.text_config.vocab_size)  # dp coordinate
     resident = to_device(host, dev)

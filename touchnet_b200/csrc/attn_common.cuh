@@ -37,8 +37,17 @@ __host__ __device__ inline int64_t attn_meta_flags_off(int B, int nblk) { return
 __host__ __device__ inline int64_t attn_meta_seg_off(int B, int nblk) {
   return (attn_meta_flags_off(B, nblk) + B + 3) / 4 * 4;
 }
-__host__ __device__ inline int64_t attn_meta_total(int B, int nblk) {
+// cost-ordered work lists of the persistent kernels (entries b*nblk + blk, heaviest first):
+//   order_q  : q blocks by kv_end - kv_lo      (forward, dQ)
+//   order_kv : kv blocks by q_end - blk        (dK/dV)
+__host__ __device__ inline int64_t attn_meta_order_off(int B, int nblk) {
   return attn_meta_seg_off(B, nblk) + int64_t(B) * nblk * ATT_BLK * 2;
+}
+__host__ __device__ inline int64_t attn_meta_order_kv_off(int B, int nblk) {
+  return attn_meta_order_off(B, nblk) + int64_t(B) * nblk;
+}
+__host__ __device__ inline int64_t attn_meta_total(int B, int nblk) {
+  return attn_meta_order_kv_off(B, nblk) + int64_t(B) * nblk;
 }
 
 // explicit shared-state-space accesses (generic LD/ST through a pointer derived from the dynamic smem base cost an

@@ -16,6 +16,8 @@
 #include "attn_common.cuh"
 #include "host.h"
 
+#include <stdlib.h>
+
 namespace tn {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -195,8 +197,30 @@ __global__ void __launch_bounds__(256) attn_meta_kernel(const int32_t* __restric
   }
 }
 
+// cost-ordered work lists (one CTA; N = B*nblk entries, rank by counting: O(N^2 / 1024) compares per thread, once per step)
+__global__ void __launch_bounds__(1024) attn_order_kernel(const AttnMeta* __restrict__ meta, int32_t* __restrict__ order_q,
+                                                          int32_t* __restrict__ order_kv, int N, int nblk) {
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const AttnMeta m = meta[i];
+    const int blk = i % nblk;
+    const int cq = m.kv_end - m.kv_lo;
+    const int ckv = m.q_end > blk ? m.q_end - blk : 0;
+    int rq = 0, rkv = 0;
+    for (int t = 0; t < N; ++t) {
+      const AttnMeta o = meta[t];
+      const int oq = o.kv_end - o.kv_lo;
+      const int ob = t % nblk;
+      const int okv = o.q_end > ob ? o.q_end - ob : 0;
+      rq += (oq > cq) || (oq == cq && t < i);
+      rkv += (okv > ckv) || (okv == ckv && t < i);
+    }
+    order_q[rq] = i;
+    order_kv[rkv] = i;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// forward kernel
+// forward kernel (round 1, one CTA per (q block, head); kept for A/B runs behind TN_ATTN_FWD_V1=1)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int FWD_THREADS = 192;
 constexpr int TILE_BYTES = ATT_BLK * ATT_HD * 2;  // 32 KB: two [128 x 128 B] swizzled chunks
@@ -547,7 +571,20 @@ extern "C" int tn_attn_prep(const int32_t* doc_ids, int32_t* meta, int B, int T,
   const int warps = B * nblk;
   attn_meta_kernel<<<(warps + 7) / 8, 256, 0, stream>>>(doc_ids, flags, reinterpret_cast<AttnMeta*>(meta), seg, B, T, nblk);
   TN_CHECK_CUDA(cudaGetLastError());
+  attn_order_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const AttnMeta*>(meta), meta + attn_meta_order_off(B, nblk),
+                                            meta + attn_meta_order_kv_off(B, nblk), B * nblk, nblk);
+  TN_CHECK_CUDA(cudaGetLastError());
   return TN_OK;
+}
+
+int attn_fwd2_launch(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                     int64_t ldo, float* lse, const int32_t* doc_ids, const int32_t* meta, int B, int T, int H, int KV,
+                     float scale, int Tq, int q_blk_off, cudaStream_t stream);
+
+static bool use_fwd_v1() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_ATTN_FWD_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
 }
 
 extern "C" int tn_attn_fwd_bf16(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
@@ -564,6 +601,8 @@ extern "C" int tn_attn_fwd_bf16(const void* Q, int64_t ldq, const void* K, int64
   if (Tq <= 0) { Tq = T; q_blk_off = 0; }
   TN_REQUIRE(q_blk_off >= 0 && q_blk_off * ATT_BLK + Tq <= nblk * ATT_BLK, "tn_attn_fwd_bf16: query window outside the sequence");
   const int nqb = (Tq + ATT_BLK - 1) / ATT_BLK;
+  if (!use_fwd_v1())
+    return attn_fwd2_launch(Q, ldq, K, ldk, V, ldv, O, ldo, lse, doc_ids, meta, B, T, H, KV, scale, Tq, q_blk_off, stream);
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   if ((rc = encode_tmap_3d(&tmQ, Q, 2, uint64_t(H) * ATT_HD, Tq, B, ldq * 2, uint64_t(Tq) * ldq * 2, 64, ATT_BLK, 1, true))) return rc;

@@ -1,0 +1,458 @@
+// touchnet_b200 :: packed-sequence ("document") causal attention, forward - persistent kernel (round 2).
+//
+// Same contract as attn_fwd.cu (replaces torch flex_attention + make_flex_block_causal_mask,
+// hf:integrations/flex_attention.py:136-247, :262-364; mask allow[b,q,k] = (q >= k) && doc[q] == doc[k] && doc[q] > 0),
+// rebuilt for the workload the ASR batches actually present (documents of a few hundred tokens: 3-4 kv blocks per
+// 128-row q block, so a one-shot CTA spends most of its life in prologue / epilogue latency):
+//
+//   * persistent CTAs (one per SM) walk a cost-ordered list of (q block, head) items; the whole (item, kv block)
+//     sequence of a CTA is ONE software pipeline: the TMA warp and the MMA warp run up to two kv blocks ahead ACROSS item
+//     boundaries (next item's Q / K arrive and its first S = Q.K^T is issued while the current item's softmax runs), and
+//     the O read-out of an item is deferred until one block of the next item has been handed to the tensor pipe;
+//   * two softmax warpgroups per q block (thread = row, each warpgroup owns 64 of the 128 score columns; row maxima
+//     meet through shared memory once per block), so a block's exp2 / convert work is spread over 8 warps;
+//   * P never touches shared memory: it is written as bf16 over the S tile it came from (tcgen05.st) and feeds the
+//     O += P.V MMA as the TMEM A operand (tcgen05.mma TS form); S is double buffered, O is double buffered per item;
+//   * O / lse leave through registers straight to global memory (each thread owns 128 contiguous bytes of a row).
+// TMEM: S0 | S1 | O0 | O1, 128 fp32 columns each = all 512.  Shared memory: 2 Q tiles + a 4-slot K/V ring (192 KB).
+#include "../../include/touchnet_b200.h"
+#include "attn_common.cuh"
+#include "host.h"
+
+namespace tn {
+
+constexpr int F2_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-5 softmax WG0, warps 6-9 softmax WG1
+constexpr int F2_TILE = ATT_BLK * ATT_HD * 2;         // 32 KB: two [128 x 128 B] swizzled chunks
+constexpr int F2_CHUNK = F2_TILE / 2;
+constexpr int F2_NKV = 4;                             // K/V ring slots (tiles alternate K, K, V, K, V, K, ...)
+constexpr int F2_MAX_ITEMS = 512;                     // schedule entries per CTA and launch
+
+struct F2Smem {
+  static constexpr int Q = 0;                              // 2 tiles (item parity)
+  static constexpr int KV = Q + 2 * F2_TILE;               // F2_NKV tiles
+  static constexpr int SMAX = KV + F2_NKV * F2_TILE;       // float [2 block parity][2 wg][128]
+  static constexpr int SL = SMAX + 2 * 2 * 128 * 4;        // float [2 item parity][2 wg][128]
+  static constexpr int DOCK = SL + 2 * 2 * 128 * 4;        // int32 [2][128]   (non-canonical ids only)
+  static constexpr int SCHED = DOCK + 2 * 128 * 4;         // int4 [F2_MAX_ITEMS]
+  static constexpr int BARS = SCHED + F2_MAX_ITEMS * 16;
+  static constexpr int TOTAL = BARS + 256;
+  static constexpr int ALLOC = TOTAL + 1024;
+};
+
+struct AttnFwd2Params {
+  const int32_t* doc;
+  const AttnMeta* meta;
+  const AttnSeg* seg;
+  const int32_t* order;   // cost-sorted (b*nblk + blk) list over the whole sequence, or NULL (context-parallel window)
+  float* lse;
+  bf16* O;
+  int64_t ldo;
+  int B, T, H, KV, nblk;
+  int Tq, q_blk_off, nqb;
+  int item_begin, item_end;  // this launch covers items [item_begin, item_end) of the B*nqb*H list
+  float scale_log2;
+};
+
+// one schedule entry: x = b << 16 | h, y = local q block, z = kv_lo, w = number of kv blocks (0: all rows are padding)
+__device__ __forceinline__ int4 f2_sched(const uint8_t* smem, int k) {
+  return *reinterpret_cast<const int4*>(smem + F2Smem::SCHED + k * 16);
+}
+
+// position in the flat (item, kv block) sequence of this CTA
+struct F2Cursor {
+  int k;        // schedule index of the current item
+  int j, n;     // kv block inside the item, number of kv blocks
+  int ip;       // running index of non-empty items (Q / O buffer parity)
+  int bh, qb_loc, kv_lo;
+  bool valid;
+};
+__device__ __forceinline__ void f2_seek(const uint8_t* smem, int nk, F2Cursor& c) {   // first non-empty item at or after c.k
+  while (c.k < nk) {
+    const int4 e = f2_sched(smem, c.k);
+    if (e.w > 0) { c.bh = e.x; c.qb_loc = e.y; c.kv_lo = e.z; c.n = e.w; c.j = 0; c.valid = true; return; }
+    ++c.k;
+  }
+  c.valid = false;
+}
+__device__ __forceinline__ void f2_init(const uint8_t* smem, int nk, F2Cursor& c) { c.k = 0; c.ip = 0; f2_seek(smem, nk, c); }
+__device__ __forceinline__ void f2_next(const uint8_t* smem, int nk, F2Cursor& c) {
+  if (++c.j < c.n) return;
+  ++c.k; ++c.ip;
+  f2_seek(smem, nk, c);
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnFwd2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + F2Smem::Q;
+  uint8_t* sKV = smem + F2Smem::KV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F2Smem::BARS);
+  uint64_t* q_full = bars + 0;     // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* kv_full = bars + 4;    // [F2_NKV]
+  uint64_t* kv_empty = bars + 8;   // [F2_NKV]
+  uint64_t* s_full = bars + 12;    // [2]
+  uint64_t* p_full = bars + 14;    // [2]  (8 warp arrivals)
+  uint64_t* pv_done = bars + 16;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const int G = p.H / p.KV;
+
+  // ---------------- schedule of this CTA: items blockIdx.x, +gridDim.x, ... of the cost-ordered list ----------------
+  const int n_launch = p.item_end - p.item_begin;
+  const int nk = (n_launch > int(blockIdx.x)) ? (n_launch - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+  for (int k = threadIdx.x; k < nk; k += F2_THREADS) {
+    const int idx = p.item_begin + int(blockIdx.x) + k * int(gridDim.x);
+    const int s = idx / p.H, h = idx - s * p.H;
+    int b, qb_loc;
+    if (p.order) { const int e = p.order[s]; b = e / p.nblk; qb_loc = e - b * p.nblk; }
+    else { b = s / p.nqb; qb_loc = p.nqb - 1 - (s - b * p.nqb); }           // latest (heaviest) q blocks first
+    const AttnMeta m = p.meta[b * p.nblk + qb_loc + p.q_blk_off];
+    *reinterpret_cast<int4*>(smem + F2Smem::SCHED + k * 16) = make_int4((b << 16) | h, qb_loc, m.kv_lo, m.kv_end - m.kv_lo);
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 8); mbar_init(&pv_done[s], 1);
+    }
+    for (int s = 0; s < F2_NKV; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: Q per item; K/V tiles in the order the MMA warp consumes them =============
+    if (lane == 0) {
+      F2Cursor a, c;                       // a: next K tile (runs two blocks ahead), c: next V tile
+      f2_init(smem, nk, a);
+      f2_init(smem, nk, c);
+      uint32_t rc = 0;                     // ring tile counter
+      auto load_tile = [&](const CUtensorMap* tm, int kvh, int row0, int b) {
+        const uint32_t s = rc % F2_NKV;
+        mbar_wait(&kv_empty[s], ((rc / F2_NKV) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], F2_TILE);
+        tma_load_3d(sKV + s * F2_TILE, tm, &kv_full[s], kvh * ATT_HD, row0, b, kEvictLast);
+        tma_load_3d(sKV + s * F2_TILE + F2_CHUNK, tm, &kv_full[s], kvh * ATT_HD + 64, row0, b, kEvictLast);
+        ++rc;
+      };
+      auto load_k = [&]() {                // K tile of cursor a (+ the item's Q when it is the item's first block)
+        const int b = a.bh >> 16, h = a.bh & 0xffff;
+        if (a.j == 0) {
+          const int qs = a.ip & 1;
+          mbar_wait(&q_empty[qs], ((a.ip >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[qs], F2_TILE);
+          tma_load_3d(sQ + qs * F2_TILE, &tmQ, &q_full[qs], h * ATT_HD, a.qb_loc * ATT_BLK, b, kEvictFirst);
+          tma_load_3d(sQ + qs * F2_TILE + F2_CHUNK, &tmQ, &q_full[qs], h * ATT_HD + 64, a.qb_loc * ATT_BLK, b, kEvictFirst);
+        }
+        load_tile(&tmK, h / G, (a.kv_lo + a.j) * ATT_BLK, b);
+        f2_next(smem, nk, a);
+      };
+      if (a.valid) load_k();
+      if (a.valid) load_k();
+      while (c.valid) {
+        load_tile(&tmV, (c.bh & 0xffff) / G, (c.kv_lo + c.j) * ATT_BLK, c.bh >> 16);
+        f2_next(smem, nk, c);
+        if (a.valid) load_k();
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);    // S = Q K^T : both K-major
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);   // O += P V : P from TMEM, V MN-major (hd contiguous)
+      F2Cursor a, c;
+      f2_init(smem, nk, a);
+      f2_init(smem, nk, c);
+      uint32_t rc = 0, gs = 0;             // ring tile counter; S tiles issued
+      auto issue_s = [&]() {
+        const int qs = a.ip & 1;
+        if (a.j == 0) mbar_wait(&q_full[qs], (a.ip >> 1) & 1);
+        const uint32_t s = rc % F2_NKV;
+        mbar_wait(&kv_full[s], (rc / F2_NKV) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + qs * F2_TILE), k_addr = smem_u32(sKV + s * F2_TILE);
+        const uint32_t d = tmem_base + (gs & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < ATT_HD / 16; ++k) {
+          const uint32_t off = (k >> 2) * F2_CHUNK + (k & 3) * 32;
+          umma_ss(d, make_sdesc_sw128(q_addr + off, 0, 1024), make_sdesc_sw128(k_addr + off, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(&s_full[gs & 1]);
+        if (a.j == a.n - 1) umma_commit(&q_empty[qs]);     // last S of the item: its Q tile may be overwritten
+        ++rc; ++gs;
+        f2_next(smem, nk, a);
+      };
+      if (a.valid) issue_s();
+      if (a.valid) issue_s();
+      for (uint32_t g = 0; c.valid; ++g) {
+        mbar_wait(&p_full[g & 1], (g >> 1) & 1);
+        const uint32_t s = rc % F2_NKV;
+        mbar_wait(&kv_full[s], (rc / F2_NKV) & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sKV + s * F2_TILE);
+        const uint32_t pbase = tmem_base + (g & 1) * 128;          // P lives over S: WG0 columns [0,32), WG1 columns [64,96)
+        const uint32_t o_t = tmem_base + 256 + (c.ip & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < ATT_BLK / 16; ++k) {
+          const uint32_t a_t = pbase + (k >> 2) * 64 + (k & 3) * 8;
+          umma_ts(o_t, a_t, make_sdesc_sw128(v_addr + k * 2048, F2_CHUNK, 1024), idesc_pv, (c.j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(&pv_done[g & 1]);
+        ++rc;
+        f2_next(smem, nk, c);
+        if (a.valid) issue_s();
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax / epilogue: 2 warpgroups, thread = q row, warpgroup = 64-column half ==============
+    const int wg = (int(warp) - 2) >> 2;
+    const uint32_t quad = warp & 3u;
+    const uint32_t r = quad * 32 + lane;              // row inside the q block == TMEM lane
+    const uint32_t lane_sel = (quad * 32u) << 16;
+    const int tid2 = int(threadIdx.x) - 64;           // 0..255 over both warpgroups
+    float* sMax = reinterpret_cast<float*>(smem + F2Smem::SMAX);
+    float* sL = reinterpret_cast<float*>(smem + F2Smem::SL);
+    const uint32_t sDocK_u32 = smem_u32(smem + F2Smem::DOCK);
+    const float NEG_INF = -INFINITY;
+    const int c_base = wg * 64;                       // first score column of this warpgroup
+
+    // pending (deferred) epilogue of the previous item
+    bool pend = false;
+    int pend_bh = 0, pend_q0l = 0, pend_ip = 0;
+    uint32_t pend_g = 0;
+    float pend_m = 0.f;
+
+    auto zero_item = [&](int bh, int qb_loc) {        // every row is padding: O = 0 exactly (FlexAttention semantics), lse = +inf
+      const int b = bh >> 16, h = bh & 0xffff;
+      const int row = qb_loc * ATT_BLK + int(r);
+      if (row < p.Tq) {
+        bf16* dst = p.O + (int64_t(b) * p.Tq + row) * p.ldo + int64_t(h) * ATT_HD + c_base;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(dst + u * 8) = make_uint4(0, 0, 0, 0);
+        if (wg == 0) p.lse[(int64_t(b) * p.H + h) * p.Tq + row] = __int_as_float(0x7f800000);
+      }
+    };
+    auto epilogue = [&]() {                           // O[pend_ip & 1] / l -> bf16 -> global; lse
+      mbar_wait(&pv_done[pend_g & 1], (pend_g >> 1) & 1);
+      tc_fence_after();
+      const float* l2 = sL + (pend_ip & 1) * 256;
+      const float l_run = l2[r] + l2[128 + r];
+      const float inv_l = (l_run > 0.f) ? 1.f / l_run : 0.f;
+      const int b = pend_bh >> 16, h = pend_bh & 0xffff;
+      const int row = pend_q0l + int(r);
+      const uint32_t o_t = tmem_base + 256 + (pend_ip & 1) * 128 + lane_sel + c_base;
+      bf16* dst = p.O + (int64_t(b) * p.Tq + row) * p.ldo + int64_t(h) * ATT_HD + c_base;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t o[32];
+        tmem_ld32(o_t + c2 * 32, o);
+        tmem_ld_wait();
+        if (row < p.Tq) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              w[e] = pack_bf16x2(__uint_as_float(o[u * 8 + 2 * e]) * inv_l, __uint_as_float(o[u * 8 + 2 * e + 1]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + c2 * 32 + u * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      if (wg == 0 && row < p.Tq)
+        p.lse[(int64_t(b) * p.H + h) * p.Tq + row] =
+            (l_run > 0.f) ? (pend_m + log2f(l_run)) * 0.6931471805599453f : __int_as_float(0x7f800000);
+      pend = false;
+    };
+
+    uint32_t g = 0;                                   // blocks processed by this CTA (S / P buffer parity, barrier phases)
+    int ip = 0;                                       // non-empty items started
+    for (int k = 0; k < nk; ++k) {
+      const int4 e = f2_sched(smem, k);
+      if (e.w == 0) { zero_item(e.x, e.y); continue; }
+      const int bh = e.x, qb_loc = e.y, kv_lo = e.z, n = e.w;
+      const int b = bh >> 16;
+      const int qb = qb_loc + p.q_blk_off;            // global block index (doc / seg / masking)
+      const int q0 = qb * ATT_BLK;
+      const int qpos = q0 + int(r);
+      const int32_t* docb = p.doc + int64_t(b) * p.T;
+      const int canonical = p.meta[b * p.nblk + qb].canonical;
+      const int32_t dq = (qpos < p.T) ? docb[qpos] : 0;
+      const int32_t dq_last = (q0 + ATT_BLK - 1 < p.T) ? docb[q0 + ATT_BLK - 1] : 0;   // uniform
+      const AttnSeg myseg = (qpos < p.T) ? p.seg[int64_t(b) * p.nblk * ATT_BLK + qpos] : AttnSeg{qpos + 1, qpos};
+      float m_run = NEG_INF, l_part = 0.f;
+
+      for (int j = 0; j < n; ++j, ++g) {
+        const int kb = kv_lo + j;
+        const int k0 = kb * ATT_BLK;
+        const bool full = canonical && (kb < qb) && (dq_last > 0) && (docb[k0] == dq_last);
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        if (!canonical) {
+          // exact element-wise document-id compare: stage the 128 key ids of this block (buffer parity = block parity)
+          if (tid2 < 128) sts_u32(sDocK_u32 + (g & 1) * 512 + tid2 * 4, uint32_t((k0 + tid2 < p.T) ? docb[k0 + tid2] : -1));
+          named_bar_sync(2, 256);
+        }
+        const uint32_t s_addr = tmem_base + (g & 1) * 128 + lane_sel + c_base;
+        uint32_t v[2][32];
+        tmem_ld32(s_addr, v[0]);
+        tmem_ld32(s_addr + 32, v[1]);
+        tmem_ld_wait();
+        float mx = NEG_INF;
+        if (full) {
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c2][i]));
+        } else if (canonical) {
+          const int lo = myseg.start - k0 - c_base, hi = qpos - k0 - c_base;   // allowed local columns: lo <= c <= hi
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = c2 * 32 + i;
+              const float x = (c >= lo && c <= hi) ? __uint_as_float(v[c2][i]) : NEG_INF;
+              v[c2][i] = __float_as_uint(x);
+              mx = fmaxf(mx, x);
+            }
+        } else {
+          const uint32_t dk_u32 = sDocK_u32 + (g & 1) * 512 + c_base * 4;
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const uint4 d4 = lds_u4(dk_u32 + (c2 * 32 + i4 * 4) * 4);
+              const int32_t dd[4] = {int32_t(d4.x), int32_t(d4.y), int32_t(d4.z), int32_t(d4.w)};
+#pragma unroll
+              for (int ee = 0; ee < 4; ++ee) {
+                const int c = c_base + c2 * 32 + i4 * 4 + ee;
+                const bool ok = (k0 + c <= qpos) && (dd[ee] == dq) && (dq > 0);
+                const float x = ok ? __uint_as_float(v[c2][i4 * 4 + ee]) : NEG_INF;
+                v[c2][i4 * 4 + ee] = __float_as_uint(x);
+                mx = fmaxf(mx, x);
+              }
+            }
+        }
+        // ---- row maximum over both halves (the other warpgroup holds the other 64 columns of this row) ----
+        float* mxb = sMax + (g & 1) * 256;
+        mxb[wg * 128 + r] = mx;
+        named_bar_sync(1, 256);
+        mx = fmaxf(mx, mxb[(wg ^ 1) * 128 + r]);
+        mx *= p.scale_log2;                           // scale > 0: max commutes with the scaling (-inf stays -inf)
+        // lazy rescale: keep the old reference max unless it grew by more than 2^8 (identical decision in both halves)
+        float m_new = m_run, alpha = 1.f;
+        if (mx > m_run + 8.f || (m_run == NEG_INF && mx > NEG_INF)) {
+          m_new = mx;
+          alpha = fast_exp2(m_run - m_new);           // m_run = -inf -> 0
+        }
+        const float m_use = (m_new == NEG_INF) ? 0.f : m_new;
+        // ---- rescale this warpgroup's 64 columns of O when a row of the warp needs it (previous P.V must have landed) ----
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+          mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+          tc_fence_after();
+          const uint32_t o_t = tmem_base + 256 + (ip & 1) * 128 + lane_sel + c_base;
+#pragma unroll 1
+          for (int c2 = 0; c2 < 2; ++c2) {
+            uint32_t o[32];
+            tmem_ld32(o_t + c2 * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(o_t + c2 * 32, o);
+          }
+        }
+        // ---- p = exp2(s*scale - m), packed to bf16 in place; masked entries are -inf -> 0 ----
+        float psum0 = 0.f, psum1 = 0.f;
+        uint32_t pk[32];
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c2][2 * i]), p.scale_log2, -m_use));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[c2][2 * i + 1]), p.scale_log2, -m_use));
+            psum0 += p0;
+            psum1 += p1;
+            pk[c2 * 16 + i] = pack_bf16x2(p0, p1);
+          }
+        l_part = l_part * alpha + (psum0 + psum1);
+        m_run = m_new;
+        // ---- P -> TMEM over this warpgroup's half of the S tile (A operand of the P.V MMA) ----
+        tmem_st32(tmem_base + (g & 1) * 128 + lane_sel + c_base, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g & 1]);
+        // ---- the previous item's O is surely complete by now: write it out while the tensor pipe works on this block ----
+        if (pend) epilogue();
+      }
+      // item finished: park its epilogue behind the first block of the next item
+      sL[(ip & 1) * 256 + wg * 128 + r] = l_part;
+      pend = true; pend_bh = bh; pend_q0l = qb_loc * ATT_BLK; pend_ip = ip; pend_g = g - 1; pend_m = m_run;
+      ++ip;
+    }
+    if (pend) {
+      named_bar_sync(1, 256);                         // the other half's row sums of the last item
+      epilogue();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace tn
+
+using namespace tn;
+
+// launched by tn_attn_fwd_bf16 (attn_fwd.cu)
+int attn_fwd2_launch(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* O,
+                     int64_t ldo, float* lse, const int32_t* doc_ids, const int32_t* meta, int B, int T, int H, int KV,
+                     float scale, int Tq, int q_blk_off, cudaStream_t stream) {
+  const int nblk = (T + ATT_BLK - 1) / ATT_BLK;
+  const int nqb = (Tq + ATT_BLK - 1) / ATT_BLK;
+  TN_REQUIRE(B < 32768 && H < 65536, "tn_attn_fwd_bf16: B / H too large for the packed schedule entry");
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = encode_tmap_3d(&tmQ, Q, 2, uint64_t(H) * ATT_HD, Tq, B, ldq * 2, uint64_t(Tq) * ldq * 2, 64, ATT_BLK, 1, true))) return rc;
+  if ((rc = encode_tmap_3d(&tmK, K, 2, uint64_t(KV) * ATT_HD, T, B, ldk * 2, uint64_t(T) * ldk * 2, 64, ATT_BLK, 1, true))) return rc;
+  if ((rc = encode_tmap_3d(&tmV, V, 2, uint64_t(KV) * ATT_HD, T, B, ldv * 2, uint64_t(T) * ldv * 2, 64, ATT_BLK, 1, true))) return rc;
+  AttnFwd2Params p{};
+  p.doc = doc_ids; p.meta = reinterpret_cast<const AttnMeta*>(meta); p.lse = lse;
+  p.seg = reinterpret_cast<const AttnSeg*>(meta + attn_meta_seg_off(B, nblk));
+  p.order = (Tq == T && q_blk_off == 0) ? meta + attn_meta_order_off(B, nblk) : nullptr;
+  p.O = static_cast<bf16*>(O); p.ldo = ldo;
+  p.B = B; p.T = T; p.H = H; p.KV = KV; p.nblk = nblk;
+  p.Tq = Tq; p.q_blk_off = q_blk_off; p.nqb = nqb;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static bool configured = false;
+  if (!configured) {
+    TN_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Smem::ALLOC));
+    configured = true;
+  }
+  const int64_t total = int64_t(B) * nqb * H;
+  const int sms = sm_count();
+  const int64_t per_launch = int64_t(sms) * F2_MAX_ITEMS;
+  for (int64_t start = 0; start < total; start += per_launch) {
+    const int64_t end = start + per_launch < total ? start + per_launch : total;
+    p.item_begin = int(start); p.item_end = int(end);
+    const int grid = int(end - start < sms ? end - start : sms);
+    attn_fwd2_kernel<<<grid, F2_THREADS, F2Smem::ALLOC, stream>>>(tmQ, tmK, tmV, p);
+    TN_CHECK_CUDA(cudaGetLastError());
+  }
+  return TN_OK;
+}

@@ -56,6 +56,11 @@ mp = MixedPrecisionPolicy(param_dtype=None if fp32_params else torch.bfloat16, r
 for layer in model.model.layers:
     fully_shard(layer, mesh=mesh, mp_policy=mp)
 fully_shard(model, mesh=mesh, mp_policy=mp)
+if os.environ.get("TN_FSDP_PEER", "0") != "0":                   # our pull kernels over NVLink peer memory instead of NCCL
+    from touchnet_b200 import fsdp_comm
+    fsdp_comm.install(model, mesh.get_group(), dev, max_ctas=int(os.environ.get("TN_FSDP_PEER_CTAS", "32")))
+    if rank == 0:
+        print("FSDP2 collectives: tn_peer_reduce_scatter_f32 / tn_peer_all_gather over symmetric memory")
 loss = step(model, slice(rank, rank + 1))
 loss.backward()
 tot = loss.detach().clone()

@@ -22,6 +22,7 @@ _SIGNATURES = {
     "tn_device_check": [],
     "tn_set_sm_margin": [_i],
     "tn_set_gemm_group": [_i],
+    "tn_set_gemm_l2_hints": [_i],
     "tn_gemm_bf16": [_vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _vp],
     "tn_gemm_swiglu_bf16": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
     "tn_gemm_qkv_bf16": [_i, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp,

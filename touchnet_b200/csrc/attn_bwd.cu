@@ -82,6 +82,86 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   }
 }
 
+
+// One 128 x 64 tile of the softmax gradient: thread = resident row, 64 streamed columns, handled as two 32-column halves.
+//   p = exp2(x*scale_log2 - lse2)  (masked -> 0),  ds = p * (y - delta);  both packed to bf16 pairs.
+// MASK 0: no mask; 1: allowed columns form the range [lo, hi]; 2: element-wise document-id compare (ids that are not
+// non-decreasing runs).  Column vectors (lse2 | delta | doc, 64 entries each) sit in shared memory at `col_u32`; for dQ
+// (DKDV = false) lse2 / delta are the thread's own row values.  Straight-line code per variant: a per-element branch
+// serialises the MUFU chain (round 1 had one and ran the loop ~8x slower than the tensor pipe).
+template <bool DKDV, int MASK>
+__device__ __forceinline__ void bwd_half(int half, uint32_t x_t, uint32_t y_t, uint32_t col_u32, int lo, int hi,
+                                         int32_t self_doc, int self_pos, int c0, float self_lse2, float self_delta,
+                                         float scale_log2, uint32_t (&pk)[32], uint32_t (&dk)[32]) {
+  uint32_t xv[32], yv[32];
+  tmem_ld32(x_t + half * 32, xv);
+  tmem_ld32(y_t + half * 32, yv);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i4 = 0; i4 < 8; ++i4) {
+    const int cb = half * 32 + i4 * 4;
+    float l2[4] = {self_lse2, self_lse2, self_lse2, self_lse2};
+    float dl[4] = {self_delta, self_delta, self_delta, self_delta};
+    if (DKDV) {
+      const uint4 a = lds_u4(col_u32 + cb * 4), b = lds_u4(col_u32 + SUB * 4 + cb * 4);
+      l2[0] = __uint_as_float(a.x); l2[1] = __uint_as_float(a.y); l2[2] = __uint_as_float(a.z); l2[3] = __uint_as_float(a.w);
+      dl[0] = __uint_as_float(b.x); dl[1] = __uint_as_float(b.y); dl[2] = __uint_as_float(b.z); dl[3] = __uint_as_float(b.w);
+    }
+    int32_t id[4] = {0, 0, 0, 0};
+    if (MASK == 2) {
+      const uint4 d = lds_u4(col_u32 + 2 * SUB * 4 + cb * 4);
+      id[0] = int32_t(d.x); id[1] = int32_t(d.y); id[2] = int32_t(d.z); id[3] = int32_t(d.w);
+    }
+    float pe[4], de[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = cb + e;
+      bool ok = true;
+      if (MASK == 1) ok = (c >= lo) & (c <= hi);
+      if (MASK == 2) {
+        const int col_pos = c0 + c;
+        ok = (DKDV ? (self_pos <= col_pos) : (col_pos <= self_pos)) & (id[e] == self_doc) & (self_doc > 0);
+      }
+      const float xs = ok ? __uint_as_float(xv[i4 * 4 + e]) : -INFINITY;     // masked -> exp2(-inf) = 0
+      pe[e] = fast_exp2(fmaf(xs, scale_log2, -l2[e]));
+      de[e] = pe[e] * (__uint_as_float(yv[i4 * 4 + e]) - dl[e]);
+    }
+    pk[cb >> 1] = pack_bf16x2(pe[0], pe[1]);
+    pk[(cb >> 1) + 1] = pack_bf16x2(pe[2], pe[3]);
+    dk[cb >> 1] = pack_bf16x2(de[0], de[1]);
+    dk[(cb >> 1) + 1] = pack_bf16x2(de[2], de[3]);
+  }
+}
+
+// MODE 0: block pair inside one document, off the diagonal (no mask); 1: canonical ids - every 32-column half is
+// classified per WARP (all rows allow every column -> no compares; no row allows any -> zeros, no TMEM read, no exp2;
+// else range compares); 2: element-wise ids.
+template <bool DKDV, int MODE>
+__device__ __forceinline__ void bwd_softmax_grad(uint32_t x_t, uint32_t y_t, uint32_t col_u32, int lo, int hi,
+                                                 int32_t self_doc, int self_pos, int c0, float self_lse2,
+                                                 float self_delta, float scale_log2, uint32_t (&pk)[32],
+                                                 uint32_t (&dk)[32]) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if (MODE == 0) {
+      bwd_half<DKDV, 0>(half, x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, scale_log2, pk, dk);
+    } else if (MODE == 2) {
+      bwd_half<DKDV, 2>(half, x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, scale_log2, pk, dk);
+    } else {
+      const bool fa = (lo <= half * 32) && (hi >= half * 32 + 31);
+      const bool em = (hi < half * 32) || (lo > half * 32 + 31) || (lo > hi);
+      if (__all_sync(0xffffffffu, em)) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { pk[half * 16 + i] = 0u; dk[half * 16 + i] = 0u; }
+      } else if (__all_sync(0xffffffffu, fa)) {
+        bwd_half<DKDV, 0>(half, x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, scale_log2, pk, dk);
+      } else {
+        bwd_half<DKDV, 1>(half, x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, scale_log2, pk, dk);
+      }
+    }
+  }
+}
+
 // DKDV = true : resident (R1,R2) = (K,V) block `blk` of kv head `hy`; streamed (T1,T2) = (Q,dO) 64-row sub-blocks
 // DKDV = false: resident (R1,R2) = (Q,dO) block `blk` of head `hy`;   streamed (T1,T2) = (K,V) 64-row sub-blocks
 template <bool DKDV>
@@ -304,39 +384,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       const uint32_t x_t = tmem_base + (t & 1) * 128 + lane_sel, y_t = x_t + 64;
       uint32_t pk[32], dk[32];
       const int lo = range_lo_pos - c0, hi = range_hi_pos - c0;   // allowed streamed columns: lo <= c <= hi
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t xv[32], yv[32];
-        tmem_ld32(x_t + half * 32, xv);
-        tmem_ld32(y_t + half * 32, yv);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pe[2], de[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = half * 32 + i + e;
-            bool ok = true;
-            if (!full) {
-              if (meta.canonical) {
-                ok = (c >= lo) && (c <= hi);
-              } else {
-                const int col_pos = c0 + c;
-                const bool causal = DKDV ? (self_pos <= col_pos) : (col_pos <= self_pos);
-                ok = causal && (col_doc[c] == self_doc) && (self_doc > 0);
-              }
-            }
-            const float l2 = DKDV ? col_lse2[c] : self_lse2;
-            const float dl = DKDV ? col_delta[c] : self_delta;
-            const float xs = ok ? __uint_as_float(xv[i + e]) : -INFINITY;       // masked -> exp2(-inf) = 0
-            const float pv = fast_exp2(fmaf(xs, p.scale_log2, -l2));
-            pe[e] = pv;
-            de[e] = pv * (__uint_as_float(yv[i + e]) - dl);
-          }
-          pk[(half * 32 + i) >> 1] = pack_bf16x2(pe[0], pe[1]);
-          dk[(half * 32 + i) >> 1] = pack_bf16x2(de[0], de[1]);
-        }
-      }
+      const uint32_t col_u32 = smem_u32(col);
+      // straight-line element code per mask mode (mode is warp-uniform; a per-element branch serialises the MUFU chain)
+      if (full) bwd_softmax_grad<DKDV, 0>(x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, p.scale_log2, pk, dk);
+      else if (meta.canonical) bwd_softmax_grad<DKDV, 1>(x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, p.scale_log2, pk, dk);
+      else bwd_softmax_grad<DKDV, 2>(x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, p.scale_log2, pk, dk);
       if (t >= 2) mbar_wait(&acc_done[t & 1], ((t >> 1) - 1) & 1);  // MMAs of iteration t-2 have consumed this group's tiles
 #pragma unroll
       for (int u = 0; u < 8; ++u) {

@@ -53,7 +53,7 @@ struct AttnFwd2Params {
   float scale_log2;
 };
 
-// one schedule entry: x = b << 16 | h, y = local q block, z = kv_lo, w = number of kv blocks (0: all rows are padding)
+// one schedule entry: x = b << 16 | h, y = local q block | canonical << 30, z = kv_lo, w = number of kv blocks (0: padding only)
 __device__ __forceinline__ int4 f2_sched(const uint8_t* smem, int k) {
   return *reinterpret_cast<const int4*>(smem + F2Smem::SCHED + k * 16);
 }
@@ -69,7 +69,7 @@ struct F2Cursor {
 __device__ __forceinline__ void f2_seek(const uint8_t* smem, int nk, F2Cursor& c) {   // first non-empty item at or after c.k
   while (c.k < nk) {
     const int4 e = f2_sched(smem, c.k);
-    if (e.w > 0) { c.bh = e.x; c.qb_loc = e.y; c.kv_lo = e.z; c.n = e.w; c.j = 0; c.valid = true; return; }
+    if (e.w > 0) { c.bh = e.x; c.qb_loc = e.y & 0x3fffffff; c.kv_lo = e.z; c.n = e.w; c.j = 0; c.valid = true; return; }
     ++c.k;
   }
   c.valid = false;
@@ -111,7 +111,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (p.order) { const int e = p.order[s]; b = e / p.nblk; qb_loc = e - b * p.nblk; }
     else { b = s / p.nqb; qb_loc = p.nqb - 1 - (s - b * p.nqb); }           // latest (heaviest) q blocks first
     const AttnMeta m = p.meta[b * p.nblk + qb_loc + p.q_blk_off];
-    *reinterpret_cast<int4*>(smem + F2Smem::SCHED + k * 16) = make_int4((b << 16) | h, qb_loc, m.kv_lo, m.kv_end - m.kv_lo);
+    *reinterpret_cast<int4*>(smem + F2Smem::SCHED + k * 16) =
+        make_int4((b << 16) | h, qb_loc | (m.canonical ? (1 << 30) : 0), m.kv_lo, m.kv_end - m.kv_lo);
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
   if (warp == 1 && lane == 0) {
@@ -278,25 +279,43 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
     uint32_t g = 0;                                   // blocks processed by this CTA (S / P buffer parity, barrier phases)
     int ip = 0;                                       // non-empty items started
+    // per-row document extent of the NEXT item is fetched one item ahead (its global-memory latency is off the critical path)
+    auto item_seg = [&](int k) {
+      const int4 e = f2_sched(smem, k);
+      const int qpos = ((e.y & 0x3fffffff) + p.q_blk_off) * ATT_BLK + int(r);
+      return (e.w > 0 && qpos < p.T) ? p.seg[int64_t(e.x >> 16) * p.nblk * ATT_BLK + qpos] : AttnSeg{qpos + 1, qpos};
+    };
+    AttnSeg nxt_seg = nk > 0 ? item_seg(0) : AttnSeg{1, 0};
     for (int k = 0; k < nk; ++k) {
       const int4 e = f2_sched(smem, k);
-      if (e.w == 0) { zero_item(e.x, e.y); continue; }
-      const int bh = e.x, qb_loc = e.y, kv_lo = e.z, n = e.w;
+      const AttnSeg myseg = nxt_seg;
+      if (k + 1 < nk) nxt_seg = item_seg(k + 1);
+      if (e.w == 0) { zero_item(e.x, e.y & 0x3fffffff); continue; }
+      const int bh = e.x, qb_loc = e.y & 0x3fffffff, kv_lo = e.z, n = e.w;
+      const bool canonical = (e.y >> 30) & 1;
       const int b = bh >> 16;
       const int qb = qb_loc + p.q_blk_off;            // global block index (doc / seg / masking)
       const int q0 = qb * ATT_BLK;
       const int qpos = q0 + int(r);
       const int32_t* docb = p.doc + int64_t(b) * p.T;
-      const int canonical = p.meta[b * p.nblk + qb].canonical;
-      const int32_t dq = (qpos < p.T) ? docb[qpos] : 0;
-      const int32_t dq_last = (q0 + ATT_BLK - 1 < p.T) ? docb[q0 + ATT_BLK - 1] : 0;   // uniform
-      const AttnSeg myseg = (qpos < p.T) ? p.seg[int64_t(b) * p.nblk * ATT_BLK + qpos] : AttnSeg{qpos + 1, qpos};
+      const int32_t dq = (!canonical && qpos < p.T) ? docb[qpos] : 0;   // element-wise id compare only
       float m_run = NEG_INF, l_part = 0.f;
 
       for (int j = 0; j < n; ++j, ++g) {
         const int kb = kv_lo + j;
         const int k0 = kb * ATT_BLK;
-        const bool full = canonical && (kb < qb) && (dq_last > 0) && (docb[k0] == dq_last);
+        // canonical rows: the allowed keys of row q are the positions [seg_start(q), q]; in this warpgroup's 64 columns
+        // that is the local range [lo, hi].  Each 32-column chunk is classified per WARP (all rows allow every column /
+        // no row allows any / mixed), so interior blocks carry no mask arithmetic and fully masked chunks (above the
+        // diagonal, other documents) cost neither compares nor exp2.
+        const int lo = myseg.start - k0 - c_base, hi = qpos - k0 - c_base;
+        uint32_t cls[2];                               // 0 = full, 1 = empty, 2 = mixed
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const bool fa = canonical && (lo <= 32 * c2) && (hi >= 32 * c2 + 31);
+          const bool em = canonical && ((hi < 32 * c2) || (lo > 32 * c2 + 31) || (lo > hi));
+          cls[c2] = __all_sync(0xffffffffu, fa) ? 0u : (__all_sync(0xffffffffu, em) ? 1u : 2u);
+        }
         mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
         if (!canonical) {
@@ -306,44 +325,43 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         const uint32_t s_addr = tmem_base + (g & 1) * 128 + lane_sel + c_base;
         uint32_t v[2][32];
-        tmem_ld32(s_addr, v[0]);
-        tmem_ld32(s_addr + 32, v[1]);
+        if (cls[0] != 1u) tmem_ld32(s_addr, v[0]);
+        if (cls[1] != 1u) tmem_ld32(s_addr + 32, v[1]);
         tmem_ld_wait();
-        float mx = NEG_INF;
-        if (full) {
+        float mx4[4] = {NEG_INF, NEG_INF, NEG_INF, NEG_INF};   // four independent chains
 #pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2)
+        for (int c2 = 0; c2 < 2; ++c2) {
+          if (cls[c2] == 0u) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c2][i]));
-        } else if (canonical) {
-          const int lo = myseg.start - k0 - c_base, hi = qpos - k0 - c_base;   // allowed local columns: lo <= c <= hi
+            for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c2][i]));
+          } else if (cls[c2] == 2u) {
+            if (canonical) {
 #pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2)
+              for (int i = 0; i < 32; ++i) {
+                const int c = c2 * 32 + i;
+                const float x = (c >= lo && c <= hi) ? __uint_as_float(v[c2][i]) : NEG_INF;
+                v[c2][i] = __float_as_uint(x);
+                mx4[i & 3] = fmaxf(mx4[i & 3], x);
+              }
+            } else {
+              const uint32_t dk_u32 = sDocK_u32 + (g & 1) * 512 + (c_base + c2 * 32) * 4;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = c2 * 32 + i;
-              const float x = (c >= lo && c <= hi) ? __uint_as_float(v[c2][i]) : NEG_INF;
-              v[c2][i] = __float_as_uint(x);
-              mx = fmaxf(mx, x);
-            }
-        } else {
-          const uint32_t dk_u32 = sDocK_u32 + (g & 1) * 512 + c_base * 4;
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const uint4 d4 = lds_u4(dk_u32 + i4 * 16);
+                const int32_t dd[4] = {int32_t(d4.x), int32_t(d4.y), int32_t(d4.z), int32_t(d4.w)};
 #pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2)
-#pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              const uint4 d4 = lds_u4(dk_u32 + (c2 * 32 + i4 * 4) * 4);
-              const int32_t dd[4] = {int32_t(d4.x), int32_t(d4.y), int32_t(d4.z), int32_t(d4.w)};
-#pragma unroll
-              for (int ee = 0; ee < 4; ++ee) {
-                const int c = c_base + c2 * 32 + i4 * 4 + ee;
-                const bool ok = (k0 + c <= qpos) && (dd[ee] == dq) && (dq > 0);
-                const float x = ok ? __uint_as_float(v[c2][i4 * 4 + ee]) : NEG_INF;
-                v[c2][i4 * 4 + ee] = __float_as_uint(x);
-                mx = fmaxf(mx, x);
+                for (int ee = 0; ee < 4; ++ee) {
+                  const int c = c_base + c2 * 32 + i4 * 4 + ee;
+                  const bool ok = (k0 + c <= qpos) && (dd[ee] == dq) && (dq > 0);
+                  const float x = ok ? __uint_as_float(v[c2][i4 * 4 + ee]) : NEG_INF;
+                  v[c2][i4 * 4 + ee] = __float_as_uint(x);
+                  mx4[ee] = fmaxf(mx4[ee], x);
+                }
               }
             }
+          }
         }
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // ---- row maximum over both halves (the other warpgroup holds the other 64 columns of this row) ----
         float* mxb = sMax + (g & 1) * 256;
         mxb[wg * 128 + r] = mx;
@@ -372,19 +390,25 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tmem_st32(o_t + c2 * 32, o);
           }
         }
-        // ---- p = exp2(s*scale - m), packed to bf16 in place; masked entries are -inf -> 0 ----
+        // ---- p = exp2(s*scale - m), packed to bf16; masked entries are -inf -> 0; empty chunks are zeros without exp2 ----
         float psum0 = 0.f, psum1 = 0.f;
         uint32_t pk[32];
 #pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2)
+        for (int c2 = 0; c2 < 2; ++c2) {
+          if (cls[c2] == 1u) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c2][2 * i]), p.scale_log2, -m_use));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v[c2][2 * i + 1]), p.scale_log2, -m_use));
-            psum0 += p0;
-            psum1 += p1;
-            pk[c2 * 16 + i] = pack_bf16x2(p0, p1);
+            for (int i = 0; i < 16; ++i) pk[c2 * 16 + i] = 0u;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(v[c2][2 * i]), p.scale_log2, -m_use));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(v[c2][2 * i + 1]), p.scale_log2, -m_use));
+              psum0 += p0;
+              psum1 += p1;
+              pk[c2 * 16 + i] = pack_bf16x2(p0, p1);
+            }
           }
+        }
         l_part = l_part * alpha + (psum0 + psum1);
         m_run = m_new;
         // ---- P -> TMEM over this warpgroup's half of the S tile (A operand of the P.V MMA) ----

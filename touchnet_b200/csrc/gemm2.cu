@@ -34,6 +34,10 @@ struct PairParams {
   int M, N, K;
   int num_m, num_n, num_k;   // num_m in units of 256 rows
   int group;                 // raster: tiles walk `group` M blocks x all N blocks before moving down (L2 reuse of A)
+  // L2 policy of the operand loads: inside a raster group the `group` A strips are re-read by every wave, a B strip is
+  // consumed within about one wave and not touched again until the next group -> A evict-last, B evict-first keeps the
+  // strips that will be re-read resident in the 126 MB L2 (tn_set_gemm_l2_hints, default on)
+  uint64_t hint_a, hint_b;
   const void* R;
   int64_t ldr;
   // segmented operands: several weight tensors that are separate nn.Parameters (q/k/v projections) behave as one GEMM
@@ -136,18 +140,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             kb0 = k0 - (sg == 0 ? 0 : (sg == 1 ? p.off1 : p.off2));
           }
           if (!A_MN) {
-            tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], k0, m0);
+            tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], k0, m0, p.hint_a);
           } else {
-            tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], m0, k0);
-            tma_load_2d_pair(a_dst + 8192, &tmA, &full_bar[stage], m0 + 64, k0);
+            tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], m0, k0, p.hint_a);
+            tma_load_2d_pair(a_dst + 8192, &tmA, &full_bar[stage], m0 + 64, k0, p.hint_a);
           }
           if (EPI == 1) {
-            tma_load_2d_pair(b_dst, rank == 0 ? &tmB : &tmB2, &full_bar[stage], k0, n0);  // CTA0: gate rows, CTA1: up rows
+            tma_load_2d_pair(b_dst, rank == 0 ? &tmB : &tmB2, &full_bar[stage], k0, n0, p.hint_b);  // CTA0: gate rows, CTA1: up rows
           } else if (!B_MN) {
-            tma_load_2d_pair(b_dst, bmap, &full_bar[stage], kb0, n0);
+            tma_load_2d_pair(b_dst, bmap, &full_bar[stage], kb0, n0, p.hint_b);
           } else {
-            tma_load_2d_pair(b_dst, bmap, &full_bar[stage], n0, kb0);
-            tma_load_2d_pair(b_dst + 8192, bmap, &full_bar[stage], n0 + 64, kb0);
+            tma_load_2d_pair(b_dst, bmap, &full_bar[stage], n0, kb0, p.hint_b);
+            tma_load_2d_pair(b_dst + 8192, bmap, &full_bar[stage], n0 + 64, kb0, p.hint_b);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -433,6 +437,8 @@ int gemm_pair_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int6
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
   p.group = gemm_group();
+  p.hint_a = gemm_l2_hints() ? kEvictLast : kEvictNormal;
+  p.hint_b = gemm_l2_hints() ? kEvictFirst : kEvictNormal;
   p.R = R; p.ldr = ldr;
   CUtensorMap tmA, tmB, tmD;
   int rc;
@@ -468,6 +474,8 @@ int gemm_pair_seg_dispatch(int mode, const void* A, int64_t lda, const void* con
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
   p.group = gemm_group();
+  p.hint_a = gemm_l2_hints() ? kEvictLast : kEvictNormal;
+  p.hint_b = gemm_l2_hints() ? kEvictFirst : kEvictNormal;
   p.off1 = seg[0]; p.off2 = seg[0] + seg[1];
   CUtensorMap tmA, tmB[3], tmD[3];
   int rc;
@@ -505,6 +513,8 @@ int gemm_pair_swiglu_dispatch(const void* X, int64_t ldx, const void* Wg, const 
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + 127) / 128; p.num_k = (K + P_BK - 1) / P_BK;
   p.group = gemm_group();
+  p.hint_a = gemm_l2_hints() ? kEvictLast : kEvictNormal;
+  p.hint_b = gemm_l2_hints() ? kEvictFirst : kEvictNormal;
   CUtensorMap tmA, tmG, tmU, tmDG, tmDU, tmDH;
   int rc;
   if ((rc = encode_tmap_2d(&tmA, X, 2, uint64_t(K), uint64_t(M), uint64_t(ldx) * 2, 64, P_BM, true))) return rc;

@@ -90,6 +90,10 @@ static int g_sm_margin = 0;
 static int g_gemm_group = 8;
 
 int gemm_group() { return g_gemm_group; }
+void set_gemm_l2_hints(int on);
+static int g_gemm_l2_hints = 1;
+int gemm_l2_hints() { return g_gemm_l2_hints; }
+void set_gemm_l2_hints(int on) { g_gemm_l2_hints = on ? 1 : 0; }
 
 int sm_count() {
   static int n = 0;
@@ -119,6 +123,11 @@ int tn_set_sm_margin(int sms) {
 int tn_set_gemm_group(int m_blocks) {
   if (m_blocks < 1 || m_blocks > 64) return tn::fail(tn::TN_ERR_ARG, "tn_set_gemm_group: %d out of range [1,64]", m_blocks);
   tn::g_gemm_group = m_blocks;
+  return tn::TN_OK;
+}
+
+int tn_set_gemm_l2_hints(int on) {
+  tn::set_gemm_l2_hints(on);
   return tn::TN_OK;
 }
 

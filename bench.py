@@ -469,7 +469,7 @@ def main():
     _lib.load()
     sm_margin = int(os.environ.get("TN_SM_MARGIN", "0"))
     _lib.call("tn_set_sm_margin", sm_margin)   # leave SMs to the FSDP2 NCCL kernels so that they overlap the GEMMs
-    _lib.call("tn_set_gemm_l2_hints", int(os.environ.get("TN_GEMM_L2_HINTS", "1") != "0"))   # A/B switch
+    _lib.call("tn_set_gemm_l2_hints", int(os.environ.get("TN_GEMM_L2_HINTS", "0") != "0"))   # A/B switch
     B, T = args.batch, args.seq_len
     cfg = asr_config(args.layers)
 

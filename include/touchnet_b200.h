@@ -37,7 +37,7 @@ int tn_set_sm_margin(int sms);
 /* Tuning knob: raster group of the CTA-pair GEMM = number of 256-row M blocks whose tiles are walked across all N blocks
  * before moving on (default 8; decides which operand strips stay L2-resident between waves).  Results do not depend on it. */
 int tn_set_gemm_group(int m_blocks);
-int tn_set_gemm_l2_hints(int on);   /* 1 (default): A strips evict-last, B strips evict-first in the CTA-pair GEMM's TMA loads */
+int tn_set_gemm_l2_hints(int on);   /* 1: A strips evict-last, B strips evict-first in the CTA-pair GEMM TMA loads (default 0: measured 6 % slower) */
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GEMM  D[M,N] = A·Bᵀ (+ R)          tcgen05 / TMEM / TMA, bf16 in, fp32 accumulate.

@@ -402,7 +402,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
 
     // ---- epilogue: accumulators -> bf16 -> smem staging (streamed-tile ring is idle now) -> TMA store ----
     // group 0 writes accumulator 1 (dV | dQ), group 1 accumulator 2 (dK)
-    mbar_wait(&acc_done[(n - 1) & 1], ((n - 1) >> 1) & 1);
+    // every accumulate has landed once the LAST one has (in-order pipe).  A group first waits for its own last iteration
+    // (its own barrier, next phase in sequence), then for the last one overall: waiting on the other group's barrier
+    // directly could alias - when this group races ahead (fully masked tiles cost it almost nothing) that barrier may
+    // still be two phases behind, and a parity wait cannot tell phase k-2 from phase k.
+    {
+      const int last_own = (n - 1 >= grp) ? (n - 1) - ((n - 1 - grp) & 1) : -1;
+      if (last_own >= 0 && last_own != n - 1) mbar_wait(&acc_done[last_own & 1], (last_own >> 1) & 1);
+      mbar_wait(&acc_done[(n - 1) & 1], ((n - 1) >> 1) & 1);
+    }
     tc_fence_after();
     if (DKDV || grp == 0) {
       const uint32_t acc_t = (grp == 0 ? tmem_acc1 : tmem_acc2) + lane_sel;

@@ -223,8 +223,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t r = quad * 32 + lane;              // row inside the q block == TMEM lane
     const uint32_t lane_sel = (quad * 32u) << 16;
     const int tid2 = int(threadIdx.x) - 64;           // 0..255 over both warpgroups
-    float* sMax = reinterpret_cast<float*>(smem + F2Smem::SMAX);
-    float* sL = reinterpret_cast<float*>(smem + F2Smem::SL);
+    const uint32_t sMax_u32 = smem_u32(smem + F2Smem::SMAX);
+    const uint32_t sL_u32 = smem_u32(smem + F2Smem::SL);
     const uint32_t sDocK_u32 = smem_u32(smem + F2Smem::DOCK);
     const float NEG_INF = -INFINITY;
     const int c_base = wg * 64;                       // first score column of this warpgroup
@@ -248,8 +248,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     auto epilogue = [&]() {                           // O[pend_ip & 1] / l -> bf16 -> global; lse
       mbar_wait(&pv_done[pend_g & 1], (pend_g >> 1) & 1);
       tc_fence_after();
-      const float* l2 = sL + (pend_ip & 1) * 256;
-      const float l_run = l2[r] + l2[128 + r];
+      const uint32_t l2 = sL_u32 + (pend_ip & 1) * 1024;
+      const float l_run = __uint_as_float(lds_u32(l2 + r * 4)) + __uint_as_float(lds_u32(l2 + (128 + r) * 4));
       const float inv_l = (l_run > 0.f) ? 1.f / l_run : 0.f;
       const int b = pend_bh >> 16, h = pend_bh & 0xffff;
       const int row = pend_q0l + int(r);
@@ -363,10 +363,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // ---- row maximum over both halves (the other warpgroup holds the other 64 columns of this row) ----
-        float* mxb = sMax + (g & 1) * 256;
-        mxb[wg * 128 + r] = mx;
-        named_bar_sync(1, 256);
-        mx = fmaxf(mx, mxb[(wg ^ 1) * 128 + r]);
+        // (the two warps that own a row quadrant meet on their own 64-thread barrier: warps of other quadrants see very
+        // different mask classes on diagonal blocks and must not wait for each other here)
+        const uint32_t mxb = sMax_u32 + (g & 1) * 1024;
+        sts_u32(mxb + (wg * 128 + r) * 4, __float_as_uint(mx));
+        named_bar_sync(3 + int(quad), 64);
+        mx = fmaxf(mx, __uint_as_float(lds_u32(mxb + ((wg ^ 1) * 128 + r) * 4)));
         mx *= p.scale_log2;                           // scale > 0: max commutes with the scaling (-inf stays -inf)
         // lazy rescale: keep the old reference max unless it grew by more than 2^8 (identical decision in both halves)
         float m_new = m_run, alpha = 1.f;
@@ -421,12 +423,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (pend) epilogue();
       }
       // item finished: park its epilogue behind the first block of the next item
-      sL[(ip & 1) * 256 + wg * 128 + r] = l_part;
+      sts_u32(sL_u32 + ((ip & 1) * 256 + wg * 128 + r) * 4, __float_as_uint(l_part));
       pend = true; pend_bh = bh; pend_q0l = qb_loc * ATT_BLK; pend_ip = ip; pend_g = g - 1; pend_m = m_run;
       ++ip;
     }
     if (pend) {
-      named_bar_sync(1, 256);                         // the other half's row sums of the last item
+      named_bar_sync(3 + int(quad), 64);              // the other half's row sums of the last item
       epilogue();
     }
   }

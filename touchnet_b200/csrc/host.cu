@@ -91,7 +91,7 @@ static int g_gemm_group = 8;
 
 int gemm_group() { return g_gemm_group; }
 void set_gemm_l2_hints(int on);
-static int g_gemm_l2_hints = 1;
+static int g_gemm_l2_hints = 0;   // measured: evict-first on B costs 6 % (partner CTAs of a wave lose the strip), see profiles/README.md
 int gemm_l2_hints() { return g_gemm_l2_hints; }
 void set_gemm_l2_hints(int on) { g_gemm_l2_hints = on ? 1 : 0; }
 

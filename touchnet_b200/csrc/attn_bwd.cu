@@ -54,6 +54,10 @@ struct AttnBwdParams {
   // cos/sin [rows, 64] bf16 indexed like the output tensor's rows (NULL = gradients w.r.t. the rotated q/k)
   const bf16* rope_cos;
   const bf16* rope_sin;
+  // cost-ordered work list (tn_attn_prep: kv blocks by number of attending q blocks for dK/dV, q blocks by number of kv
+  // blocks for dQ; entries b*nblk + blk, heaviest first) walked by a 1-D grid, so that the last wave is made of the
+  // cheapest items; NULL = (block, head, batch) grid (context-parallel windows)
+  const int32_t* order;
 };
 
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ O, int64_t ldo,
@@ -190,9 +194,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   const uint32_t warp = warp_id(), lane = lane_id();
   const int q_off = p.q_blk_off * ATT_BLK;                          // global position of local query row 0
   const int nq_loc = (p.Tq + ATT_BLK - 1) / ATT_BLK;
-  const int blk_loc = DKDV ? int(blockIdx.x) : int(gridDim.x) - 1 - int(blockIdx.x);
+  int blk_loc, hy, b;
+  if (p.order) {
+    const int heads = DKDV ? p.KV : p.H;
+    const int s = int(blockIdx.x) / heads;
+    hy = int(blockIdx.x) - s * heads;
+    const int e = p.order[s];
+    b = e / p.nblk;
+    blk_loc = e - b * p.nblk;
+  } else {
+    blk_loc = DKDV ? int(blockIdx.x) : int(gridDim.x) - 1 - int(blockIdx.x);
+    hy = blockIdx.y; b = blockIdx.z;
+  }
   const int blk = DKDV ? blk_loc : blk_loc + p.q_blk_off;           // GLOBAL block index of the resident tile
-  const int hy = blockIdx.y, b = blockIdx.z;
   const int G = p.H / p.KV;
   const int r0 = blk * ATT_BLK;                                     // global position of resident row 0
   const int r0l = DKDV ? r0 : blk_loc * ATT_BLK;                    // row 0 inside the resident tensors (K/V global, Q/dO local)
@@ -237,8 +251,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   const uint32_t tmem_acc1 = tmem_base + 256, tmem_acc2 = tmem_base + 384;
 
   // iteration t -> (streamed head, streamed row0)
-  auto iter_head = [&](int t) { return DKDV ? hy * G + t / (nsb * 2) : hy / G; };
-  auto iter_row0 = [&](int t) { const int u = DKDV ? t % (nsb * 2) : t; return (sb_lo + (u >> 1)) * ATT_BLK + (u & 1) * SUB; };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -248,13 +260,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       tma_load_3d(sR1 + RES_CHUNK, &tmR1, r_full, hy * ATT_HD + 64, r0l, b);
       tma_load_3d(sR2, &tmR2, r_full, hy * ATT_HD, r0l, b);
       tma_load_3d(sR2 + RES_CHUNK, &tmR2, r_full, hy * ATT_HD + 64, r0l, b);
+      int pu = 0, phd = 0;                                             // position inside the head's streamed range, head offset
       for (int t = 0; t < n; ++t) {
         const int s = t % NST;
         mbar_wait(&t_empty[s], ((t / NST) & 1) ^ 1);
         mbar_arrive_expect_tx(&t_full[s], 2 * STR_BYTES);
         uint8_t* d1 = sT + s * 2 * STR_BYTES;
         uint8_t* d2 = d1 + STR_BYTES;
-        const int hs = iter_head(t), row0 = iter_row0(t) - s_off;   // row inside the streamed tensor
+        const int hs = DKDV ? hy * G + phd : hy / G;
+        const int row0 = (sb_lo + (pu >> 1)) * ATT_BLK + (pu & 1) * SUB - s_off;   // row inside the streamed tensor
+        if (++pu == nsb * 2 && DKDV) { pu = 0; ++phd; }
         tma_load_3d(d1, &tmT1, &t_full[s], hs * ATT_HD, row0, b);
         tma_load_3d(d1 + STR_CHUNK, &tmT1, &t_full[s], hs * ATT_HD + 64, row0, b);
         tma_load_3d(d2, &tmT2, &t_full[s], hs * ATT_HD, row0, b);
@@ -325,8 +340,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const int self_pos = r0 + int(r);
     const int32_t* docb = p.doc + int64_t(b) * p.T;
     const int32_t self_doc = (self_pos < p.T) ? docb[self_pos] : 0;
-    const int32_t res_first = docb[r0];                                            // uniform
-    const int32_t res_last = (r0 + ATT_BLK - 1 < p.T) ? docb[r0 + ATT_BLK - 1] : 0;  // uniform
     const uint32_t lane_sel = (quad * 32u) << 16;
     // canonical rows: the partner positions of this row are one contiguous range (two integer compares per element)
     //   dK/dV (thread = key k):   queries q in [k, seg_end(k))        dQ (thread = query q): keys k in [seg_start(q), q]
@@ -342,52 +355,56 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       self_delta = (lpos < p.Tq) ? p.delta[idx] : 0.f;
     }
 
-    // column vectors (doc ids; for dK/dV also lse, delta of the streamed q rows) are fetched one iteration ahead so
-    // that their global-memory latency is off the critical path
-    auto fetch_col = [&](int t, int32_t& d_out, float& f_out) {
-      const int c = tid & 63, pos = iter_row0(t) + c;
-      const int hs_ = iter_head(t);
+    // column vectors (for dK/dV: lse, delta of the streamed q rows; doc ids for the element-wise mask mode) are fetched one
+    // iteration ahead so that their global-memory latency is off the critical path.  Iterations are decoded incrementally
+    // (head offset, position inside the head's streamed range): no integer division and no dependent global load sits
+    // between two tiles (round 1 had both; together they cost more than the softmax gradient itself).
+    const int nsb2 = nsb * 2;
+    const bool need_cols = DKDV || !meta.canonical;
+    auto row0_of = [&](int u) { return (sb_lo + (u >> 1)) * ATT_BLK + (u & 1) * SUB; };
+    auto fetch_col = [&](int hd, int u, int32_t& d_out, float& f_out) {     // raw values; scaled when staged
+      const int c = tid & 63, pos = row0_of(u) + c;
+      const int hs_ = DKDV ? hy * G + hd : hy / G;
       d_out = -2; f_out = 0.f;
       if (tid < 64) {
         d_out = (pos < p.T) ? docb[pos] : -2;
-        if (DKDV) f_out = (pos - q_off < p.Tq) ? p.lse[(int64_t(b) * p.H + hs_) * p.Tq + pos - q_off] * 1.4426950408889634f
-                                               : __int_as_float(0x7f800000);
+        if (DKDV) f_out = (pos - q_off < p.Tq) ? p.lse[(int64_t(b) * p.H + hs_) * p.Tq + pos - q_off] : __int_as_float(0x7f800000);
       } else if (DKDV) {
         f_out = (pos - q_off < p.Tq) ? p.delta[(int64_t(b) * p.H + hs_) * p.Tq + pos - q_off] : 0.f;
       }
     };
+    auto adv2 = [&](int& hd, int& u) { u += 2; if (DKDV) { while (u >= nsb2) { u -= nsb2; ++hd; } } };
+    int hd_cur = 0, u_cur = grp;                       // decode of iteration t = grp (grp < 2 <= nsb2)
+    if (DKDV) { while (u_cur >= nsb2) { u_cur -= nsb2; ++hd_cur; } }
+    int hd_nxt = hd_cur, u_nxt = u_cur;
     int32_t nxt_doc = -2; float nxt_f = 0.f;
-    if (grp < n) fetch_col(grp, nxt_doc, nxt_f);
+    if (grp < n && need_cols) fetch_col(hd_cur, u_cur, nxt_doc, nxt_f);
 
     for (int t = grp; t < n; t += 2) {
-      const int c0 = iter_row0(t);
-      const int sblk = c0 / ATT_BLK;
-      // pair of 128-blocks is one document strictly off the diagonal -> no mask arithmetic
-      bool full;
-      if (DKDV) full = meta.canonical && (sblk > blk) && (res_first > 0) && (c0 / ATT_BLK * ATT_BLK + ATT_BLK - 1 < p.T) &&
-                       (docb[sblk * ATT_BLK + ATT_BLK - 1] == res_first);
-      else      full = meta.canonical && (sblk < blk) && (res_last > 0) && (docb[sblk * ATT_BLK] == res_last);
+      const int c0 = row0_of(u_cur);
       mbar_wait(&xy_full[t & 1], (t >> 1) & 1);
       tc_fence_after();
       float* col = sCol + (t & 1) * 3 * SUB;
-      float* col_lse2 = col;
-      float* col_delta = col + SUB;
-      int32_t* col_doc = reinterpret_cast<int32_t*>(col + 2 * SUB);
-      {
+      adv2(hd_nxt, u_nxt);
+      if (need_cols) {
+        float* col_lse2 = col;
+        float* col_delta = col + SUB;
+        int32_t* col_doc = reinterpret_cast<int32_t*>(col + 2 * SUB);
         const int c = tid & 63;
-        if (tid < 64) { col_doc[c] = nxt_doc; if (DKDV) col_lse2[c] = nxt_f; }
+        if (tid < 64) { col_doc[c] = nxt_doc; if (DKDV) col_lse2[c] = nxt_f * 1.4426950408889634f; }
         else if (DKDV) col_delta[c] = nxt_f;
-        if (t + 2 < n) fetch_col(t + 2, nxt_doc, nxt_f);   // in flight during this iteration's math
+        if (t + 2 < n) fetch_col(hd_nxt, u_nxt, nxt_doc, nxt_f);   // in flight during this iteration's math
+        named_bar_sync(1 + grp, 128);
       }
-      named_bar_sync(1 + grp, 128);
+      hd_cur = hd_nxt; u_cur = u_nxt;
 
       const uint32_t x_t = tmem_base + (t & 1) * 128 + lane_sel, y_t = x_t + 64;
       uint32_t pk[32], dk[32];
       const int lo = range_lo_pos - c0, hi = range_hi_pos - c0;   // allowed streamed columns: lo <= c <= hi
       const uint32_t col_u32 = smem_u32(col);
       // straight-line element code per mask mode (mode is warp-uniform; a per-element branch serialises the MUFU chain)
-      if (full) bwd_softmax_grad<DKDV, 0>(x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, p.scale_log2, pk, dk);
-      else if (meta.canonical) bwd_softmax_grad<DKDV, 1>(x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, p.scale_log2, pk, dk);
+      // canonical ids: every 32-column half is classified by warp votes on the per-row ranges held in registers
+      if (meta.canonical) bwd_softmax_grad<DKDV, 1>(x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, p.scale_log2, pk, dk);
       else bwd_softmax_grad<DKDV, 2>(x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, p.scale_log2, pk, dk);
       if (t >= 2) mbar_wait(&acc_done[t & 1], ((t >> 1) - 1) & 1);  // MMAs of iteration t-2 have consumed this group's tiles
 #pragma unroll
@@ -548,14 +565,20 @@ extern "C" int tn_attn_bwd_bf16(const void* Q, int64_t ldq, const void* K, int64
     AttnBwdParams pk = p;
     pk.out1 = static_cast<bf16*>(dV); pk.ld1 = lddv; pk.out2 = static_cast<bf16*>(dK); pk.ld2 = lddk;
     pk.rope_cos = static_cast<const bf16*>(rope_cos_k); pk.rope_sin = static_cast<const bf16*>(rope_sin_k);
-    attn_bwd_kernel<true><<<dim3(nblk, KV, B), BWD_THREADS, BwdSmem::ALLOC, stream>>>(k128, v128, q64, do64, mdv, mdk, pk);
+    const bool ordered = (Tq == T && q_blk_off == 0);
+    pk.order = ordered ? meta + attn_meta_order_kv_off(B, nblk) : nullptr;
+    const dim3 grid = ordered ? dim3(unsigned(nblk) * KV * B) : dim3(nblk, KV, B);
+    attn_bwd_kernel<true><<<grid, BWD_THREADS, BwdSmem::ALLOC, stream>>>(k128, v128, q64, do64, mdv, mdk, pk);
     TN_CHECK_CUDA(cudaGetLastError());
   }
   {
     AttnBwdParams pq = p;
     pq.out1 = static_cast<bf16*>(dQ); pq.ld1 = lddq; pq.out2 = nullptr; pq.ld2 = 0;
     pq.rope_cos = static_cast<const bf16*>(rope_cos_q); pq.rope_sin = static_cast<const bf16*>(rope_sin_q);
-    attn_bwd_kernel<false><<<dim3(nqb, H, B), BWD_THREADS, BwdSmem::ALLOC, stream>>>(q128, do128, k64, v64, mdq, mdq, pq);
+    const bool ordered = (Tq == T && q_blk_off == 0);
+    pq.order = ordered ? meta + attn_meta_order_off(B, nblk) : nullptr;
+    const dim3 grid = ordered ? dim3(unsigned(nqb) * H * B) : dim3(nqb, H, B);
+    attn_bwd_kernel<false><<<grid, BWD_THREADS, BwdSmem::ALLOC, stream>>>(q128, do128, k64, v64, mdq, mdq, pq);
     TN_CHECK_CUDA(cudaGetLastError());
   }
   return TN_OK;

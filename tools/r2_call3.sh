@@ -8,4 +8,4 @@ done
 echo "=== attn bench"
 timeout 300 python tools/attn_bench.py --case cfg2,cfg3,cfg4,cfg5 2>&1 | tail -4
 echo "=== ncu attention (set full)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 6 -c 4 -o gpurun_out/r02_attn_cfg2_b python tools/attn_bench.py --case cfg2 --iters 1 > gpurun_out/ncu_attn.log 2>&1; tail -1 gpurun_out/ncu_attn.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 6 -c 5 -o gpurun_out/r02_attn_cfg2_c python tools/attn_bench.py --case cfg2 --iters 1 > gpurun_out/ncu_attn.log 2>&1; tail -1 gpurun_out/ncu_attn.log

@@ -4,13 +4,18 @@
 // (autograd of torch.nn.attention.flex_attention with the block-causal document mask of :136-247).
 //
 // Three launches, no atomics, deterministic:
-//   attn_delta_kernel            delta[b,h,t] = Σ_d O·dO
-//   attn_bwd_kernel<true>        one CTA per (kv block, kv head): loops over the q heads of the GQA group and the
-//                                q blocks that attend to it;  Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ (TMEM), Pᵀ/dSᵀ -> smem,
-//                                dV += Pᵀ·dO, dK += dSᵀ·Q accumulate in TMEM across the whole loop.
-//   attn_bwd_kernel<false>       one CTA per (q block, head): S = Q·Kᵀ, dP = dO·Vᵀ, dS -> smem, dQ += dS·K.
-// Both use the same skeleton: two resident 128-row tiles, two streamed 64-row tiles (2-stage TMA ring), double
-// buffered score tiles in TMEM, one softmax warpgroup (thread = resident row), one MMA-issuing thread.
+//   attn_delta_kernel            delta[b,h,t] = sum_d O.dO
+//   attn_bwd_kernel<true>        one CTA per (kv block, kv head), walked heaviest first: loops over the q heads of the GQA
+//                                group and the q blocks that attend to it;  S^T = K.Q^T, dP^T = V.dO^T (TMEM),
+//                                dV += P^T.dO, dK += dS^T.Q accumulate in TMEM across the whole loop.
+//   attn_bwd_kernel<false>       one CTA per (q block, head): S = Q.K^T, dP = dO.V^T, dQ += dS.K.
+// Both use the same skeleton: two resident 128-row tiles, two streamed 64-row tiles (4-stage TMA ring), double buffered
+// score tiles in TMEM, two softmax-grad warpgroups ping-ponging over the iterations (thread = resident row), one
+// MMA-issuing thread.  P^T / dS^T never touch shared memory: they are written as bf16 over the score tiles they came
+// from (tcgen05.st) and feed the accumulate MMAs as TMEM A operands (TS form) - the SS form of these MMAs read 8 KB of
+// shared memory per 64 tensor-pipe cycles and made the kernels shared-memory-bandwidth bound.  Masking is decided per
+// warp and per 32-column half from the per-row document extents (no compares on interior tiles, no exp2 / TMEM reads on
+// fully masked ones).
 #include "../../include/touchnet_b200.h"
 #include "attn_common.cuh"
 #include "host.h"
@@ -23,16 +28,13 @@ constexpr int RES_BYTES = ATT_BLK * ATT_HD * 2;       // 32 KB resident tile (2 
 constexpr int RES_CHUNK = RES_BYTES / 2;
 constexpr int STR_BYTES = SUB * ATT_HD * 2;           // 16 KB streamed tile (2 chunks of 8 KB)
 constexpr int STR_CHUNK = STR_BYTES / 2;
-constexpr int PT_BYTES = ATT_BLK * SUB * 2;           // 16 KB  [128 rows x 128 B]
-constexpr int NST = 3;                                // streamed-tile ring depth (TMA latency hidden behind 2 iterations)
+constexpr int NST = 4;                                // streamed-tile ring depth
 
 struct BwdSmem {
   static constexpr int R1 = 0;
   static constexpr int R2 = R1 + RES_BYTES;
   static constexpr int T = R2 + RES_BYTES;                  // NST stages x (T1, T2)
-  static constexpr int PT = T + NST * 2 * STR_BYTES;         // 2 buffers (one per warpgroup)
-  static constexpr int DST = PT + 2 * PT_BYTES;             // 2 buffers
-  static constexpr int COL = DST + 2 * PT_BYTES;            // 2 x {lse2[64], delta[64], doc[64]}
+  static constexpr int COL = T + NST * 2 * STR_BYTES;        // 2 x {lse2[64], delta[64], doc[64]}
   static constexpr int BARS = COL + 2 * 3 * SUB * 4;
   static constexpr int TOTAL = BARS + 256;
   static constexpr int ALLOC = TOTAL + 1024;
@@ -179,8 +181,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
   uint8_t* sR1 = smem + BwdSmem::R1;
   uint8_t* sR2 = smem + BwdSmem::R2;
   uint8_t* sT = smem + BwdSmem::T;
-  uint8_t* sPT = smem + BwdSmem::PT;
-  uint8_t* sDST = smem + BwdSmem::DST;
   float* sCol = reinterpret_cast<float*>(smem + BwdSmem::COL);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BARS);
   uint64_t* r_full = bars + 0;
@@ -282,7 +282,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc_xy = make_idesc_bf16(128, SUB, 0, 0);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, ATT_HD, 0, 1);
-      const uint32_t r1 = smem_u32(sR1), r2 = smem_u32(sR2), pt0 = smem_u32(sPT), dst0 = smem_u32(sDST);
+      const uint32_t r1 = smem_u32(sR1), r2 = smem_u32(sR2);
       auto issue_xy = [&](int t) {
         const int s = t % NST;
         mbar_wait(&t_full[s], (t / NST) & 1);
@@ -309,19 +309,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         mbar_wait(&pds_full[t & 1], (t >> 1) & 1);
         tc_fence_after();
         const uint32_t t1 = smem_u32(sT + s * 2 * STR_BYTES), t2 = t1 + STR_BYTES;
-        const uint32_t pt = pt0 + (t & 1) * PT_BYTES, dst = dst0 + (t & 1) * PT_BYTES;
+        // P^T / dS^T are bf16 tiles the softmax-grad warps wrote OVER the score tiles they came from (TMEM A operand,
+        // tcgen05.mma TS form): columns [0,32) of the S^T and of the dP^T tile of this iteration's buffer
+        const uint32_t pt = tmem_base + (t & 1) * 128, dst = pt + 64;
 #pragma unroll
         for (int k = 0; k < SUB / 16; ++k) {
           if (DKDV) {
-            // dV += Pᵀ·dO   (B = dO tile, MN-major: hd contiguous)      dK += dSᵀ·Q
-            umma_ss(tmem_acc1, make_sdesc_sw128(pt + k * 32, 0, 1024), make_sdesc_sw128(t2 + k * 2048, STR_CHUNK, 1024),
-                    idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
-            umma_ss(tmem_acc2, make_sdesc_sw128(dst + k * 32, 0, 1024), make_sdesc_sw128(t1 + k * 2048, STR_CHUNK, 1024),
-                    idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
+            // dV += P^T.dO   (B = dO tile, MN-major: hd contiguous)      dK += dS^T.Q
+            umma_ts(tmem_acc1, pt + k * 8, make_sdesc_sw128(t2 + k * 2048, STR_CHUNK, 1024), idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
+            umma_ts(tmem_acc2, dst + k * 8, make_sdesc_sw128(t1 + k * 2048, STR_CHUNK, 1024), idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
           } else {
-            // dQ += dS·K
-            umma_ss(tmem_acc1, make_sdesc_sw128(dst + k * 32, 0, 1024), make_sdesc_sw128(t1 + k * 2048, STR_CHUNK, 1024),
-                    idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
+            // dQ += dS.K
+            umma_ts(tmem_acc1, dst + k * 8, make_sdesc_sw128(t1 + k * 2048, STR_CHUNK, 1024), idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
           }
         }
         umma_commit(&t_empty[s]);
@@ -346,7 +345,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const AttnSeg myseg = (self_pos < p.T) ? p.seg[int64_t(b) * p.nblk * ATT_BLK + self_pos] : AttnSeg{self_pos + 1, self_pos};
     const int range_lo_pos = DKDV ? self_pos : myseg.start;
     const int range_hi_pos = DKDV ? myseg.end - 1 : self_pos;
-    const uint32_t sPT_u32 = smem_u32(sPT) + grp * PT_BYTES, sDST_u32 = smem_u32(sDST) + grp * PT_BYTES;
     float self_lse2 = 0.f, self_delta = 0.f;
     if (!DKDV) {
       const int lpos = self_pos - q_off;                                // local query row
@@ -406,13 +404,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
       // canonical ids: every 32-column half is classified by warp votes on the per-row ranges held in registers
       if (meta.canonical) bwd_softmax_grad<DKDV, 1>(x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, p.scale_log2, pk, dk);
       else bwd_softmax_grad<DKDV, 2>(x_t, y_t, col_u32, lo, hi, self_doc, self_pos, c0, self_lse2, self_delta, p.scale_log2, pk, dk);
-      if (t >= 2) mbar_wait(&acc_done[t & 1], ((t >> 1) - 1) & 1);  // MMAs of iteration t-2 have consumed this group's tiles
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (DKDV) sts_u4(sPT_u32 + sw128_off(r, u), make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]));
-        sts_u4(sDST_u32 + sw128_off(r, u), make_uint4(dk[4 * u], dk[4 * u + 1], dk[4 * u + 2], dk[4 * u + 3]));
-      }
-      fence_proxy_async_smem();
+      // P^T / dS^T -> TMEM, in place over this thread's own lane of the score tiles (every value of the lane was read above;
+      // the buffer's next writer, xy(t+2), is issued behind this iteration's accumulate MMAs in the in-order tensor pipe)
+      if (DKDV) tmem_st32(x_t, pk);
+      tmem_st32(y_t, dk);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&pds_full[t & 1]);
     }

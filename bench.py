@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cp", type=int, default=1, help="context-parallel degree (BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-incumbent", action="store_true",
+                    help="skip extras.incumbent (compiled flex_attention / cuBLAS / Liger / HF layer timed next to ours, N=1)")
     args = ap.parse_args()
     select_workload(args)
     return args
@@ -208,6 +210,7 @@ class GemmTimer:
 
     def __init__(self):
         self.pairs = []
+        self.shapes = []
         self._open = None
 
     def __call__(self, name, phase, args):
@@ -221,19 +224,47 @@ class GemmTimer:
                 flops = 4.0 * args[9] * args[10] * args[11]
             elif name == "tn_gemm_qkv_bf16":
                 flops = 2.0 * args[15] * args[16] * args[17]
-            self._open = (e, flops, name)
+            elif name == "tn_gemm_dswiglu_bf16":
+                flops = 2.0 * args[10] * args[11] * args[12]
+            shape = None
+            if name == "tn_gemm_bf16":
+                shape = ("gemm", int(args[2]), int(args[5]), int(args[8]), args[11], args[12], args[13])
+            elif name == "tn_gemm_swiglu_bf16":
+                shape = ("gemm_swiglu", 0, 0, 0, args[9], 2 * args[10], args[11])
+            elif name == "tn_gemm_qkv_bf16":
+                shape = ("gemm_qkv_mode%d" % int(args[0]), 0, 0, 0, args[15], args[16], args[17])
+            elif name == "tn_gemm_dswiglu_bf16":
+                shape = ("gemm_dswiglu", 0, 1, 0, args[10], args[11], args[12])
+            self._open = (e, flops, name, shape)
         else:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             self.pairs.append((self._open[0], e1, self._open[1], self._open[2]))
+            if self._open[3] is not None:
+                self.shapes.append((self._open[0], e1, self._open[1], self._open[3]))
 
     def summary(self):
         ms = fl = 0.0
         n = 0
         for a, b, f, name in self.pairs:
-            if name in ("tn_gemm_bf16", "tn_gemm_swiglu_bf16", "tn_gemm_qkv_bf16"):
+            if name in ("tn_gemm_bf16", "tn_gemm_swiglu_bf16", "tn_gemm_qkv_bf16", "tn_gemm_dswiglu_bf16"):
                 ms += a.elapsed_time(b); fl += f; n += 1
         return ms, fl, n
+
+    def by_shape(self, peak_tflops: float):
+        """Per GEMM shape (entry point, operand majorness, fp32 output flag, M, N, K): launches, mean ms, TFLOP/s and the
+        fraction of the sustained tensor peak - the per-shape lines behind the aggregate `roofline`."""
+        acc = {}
+        for a, b, f, shp in self.shapes:
+            kind, a_mn, b_mn, f32, M, N, K = shp
+            key = f"{kind}{'_aT' if a_mn else ''}{'_bT' if b_mn else ''}{'_f32out' if f32 else ''} M={M} N={N} K={K}"
+            e = acc.setdefault(key, [0, 0.0, 0.0])
+            e[0] += 1; e[1] += a.elapsed_time(b); e[2] += f
+        out = {}
+        for k, (n, ms, fl) in sorted(acc.items(), key=lambda kv: -kv[1][1]):
+            tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            out[k] = {"launches": n, "ms_mean": round(ms / n, 4), "tflops": round(tf, 1), "frac": round(tf / peak_tflops, 3)}
+        return out
 
     def by_class(self):
         out = {}
@@ -247,8 +278,29 @@ def attn_flops_fwd_per_layer(doc_lens, H=32, hd=128):
     return 4.0 * H * hd * sum(n * (n + 1) / 2 for n in doc_lens)
 
 
+def attn_tile_flops_fwd_per_layer(doc, H=32, hd=128):
+    """tile-granular: 4*H*hd*128*128 per (q block, kv block) pair the kernels visit (what the tensor pipe executes)."""
+    tiles = 0
+    for b in range(doc.shape[0]):
+        d = doc[b]
+        T = d.numel()
+        start = torch.zeros(T, dtype=torch.long)
+        change = torch.ones(T, dtype=torch.bool)
+        change[1:] = d[1:] != d[:-1]
+        idx = torch.arange(T)
+        start = torch.cummax(torch.where(change, idx, torch.zeros_like(idx)), 0).values
+        for qb in range((T + 127) // 128):
+            rows = slice(qb * 128, min(T, (qb + 1) * 128))
+            valid = d[rows] > 0
+            if valid.any():
+                lo = int(start[rows][valid].min()) // 128
+                tiles += qb + 1 - lo
+    return 4.0 * H * hd * 128 * 128 * tiles
+
+
 def derived_columns(by_class: dict, steps: int, ms_per_step: float, attn_fwd_flop_step: float, nonpad_tokens: int,
-                    tokens_per_step: int, B: int, T: int, layers: int, peaks: dict, text: dict) -> dict:
+                    tokens_per_step: int, B: int, T: int, layers: int, peaks: dict, text: dict,
+                    attn_tile_flop_step: float = 0.0) -> dict:
     """The report columns of BASELINE.md (attention TFLOP/s and MFU, HBM GB/s of the norm / SwiGLU-backward / loss kernels,
     non-pad tokens/s, the reference's own MFU convention) from the per-entry-point device times of the timed region.
     rank 0's rows; never raises (a missing key only drops its column)."""
@@ -262,10 +314,14 @@ def derived_columns(by_class: dict, steps: int, ms_per_step: float, attn_fwd_flo
             tf = attn_fwd_flop_step / (per["tn_attn_fwd_bf16"] * 1e-3) / 1e12
             out["attn_fwd_tflops_mask_exact"] = tf
             out["attn_fwd_mfu_mask_exact"] = tf / peak
+            if attn_tile_flop_step:
+                out["attn_fwd_mfu_tile_granular"] = attn_tile_flop_step / (per["tn_attn_fwd_bf16"] * 1e-3) / 1e12 / peak
         if per.get("tn_attn_bwd_bf16"):
             tb = 2.5 * attn_fwd_flop_step / (per["tn_attn_bwd_bf16"] * 1e-3) / 1e12
             out["attn_bwd_tflops_mask_exact_2p5x"] = tb
             out["attn_bwd_mfu_mask_exact"] = tb / peak
+            if attn_tile_flop_step:
+                out["attn_bwd_mfu_tile_granular_2p5x"] = 2.5 * attn_tile_flop_step / (per["tn_attn_bwd_bf16"] * 1e-3) / 1e12 / peak
         gb = lambda bytes_, ms: bytes_ / (ms * 1e-3) / 1e9
         n_norm = 2 * layers + 1
         if per.get("tn_rmsnorm_fwd_bf16"):
@@ -510,7 +566,8 @@ def main():
         fully_shard(model, mesh=mesh, mp_policy=mp, reshard_after_forward=reshard)
         if os.environ.get("TN_FSDP_PEER", "0") != "0":   # EXPERIMENTAL: our pull kernels over NVLink peer memory instead of NCCL
             from touchnet_b200 import fsdp_comm
-            fsdp_comm.install(model, mesh.get_group(), dev, max_ctas=int(os.environ.get("TN_FSDP_PEER_CTAS", "32")))
+            fsdp_comm.install(model, mesh.get_group(), dev, max_ctas=int(os.environ.get("TN_FSDP_PEER_CTAS", "32")),
+                              mode="push" if os.environ["TN_FSDP_PEER"] == "push" else "pull")
         depth = int(os.environ.get("TN_FSDP_PREFETCH", "0"))
         if depth > 0:                                    # explicit prefetch of the next `depth` blocks' all-gathers
             for i, layer in enumerate(layers):
@@ -602,6 +659,7 @@ def main():
                      "algorithmic_bytes_per_launch": (gemm_traffic() or {}).get("avg_algorithmic_bytes_per_gemm_launch"),
                      "kernel": "tn::gemm_pair_kernel<A_MN,B_MN,EPI> (all GEMM launches of the timed region)",
                      "launches": gemm_n, "share_of_step": gemm_ms / ms if ms > 0 else None,
+                     "by_shape": gt.by_shape(peaks["bf16_sustained"]),
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); burst {peaks['bf16_burst']}"},
         "extras": {"nonpad_tokens_per_step_rank0": meta["nonpad_tokens"], "docs_rank0": len(meta["doc_lens"]),
                    "attn_fwd_tflop_mask_exact_per_step_rank0": attn_fwd / 1e12, "loss": final_loss,
@@ -609,7 +667,10 @@ def main():
                    "ms_by_entry_point_timed_region": gt.by_class(),
                    "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
                    "report_columns_rank0": derived_columns(gt.by_class(), args.steps, ms / args.steps, attn_fwd,
-                                                           meta["nonpad_tokens"], B * T, B, T, n_layers, peaks, _W["text"])},
+                                                           meta["nonpad_tokens"], B * T, B, T, n_layers, peaks, _W["text"],
+                                                           attn_tile_flops_fwd_per_layer(host["attention_mask"],
+                                                                                         _W["text"]["num_attention_heads"])
+                                                           * n_layers)},
     }
     if world == 1 and not args.no_cpu_baseline:
         state = cpu_reference_setup()
@@ -618,6 +679,18 @@ def main():
         sec = sum(ts) / len(ts)
         line["cpu_baseline"] = {"value": cpu_tokens_per_s(sec), "unit": "tokens/s", "cores": torch.get_num_threads(),
                                 "kind": "port", "sample": CPU_SAMPLE_DESC}
+    if world == 1 and not args.no_incumbent:
+        # the kernels the reference's GPU path actually resolves to (flex_attention, cuBLAS, Liger, HF eager layer), same box,
+        # same shapes, after our model is freed; never part of `value` / `--impl reference` (tools/incumbent.py)
+        try:
+            del model, resident, loss
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            from tools import incumbent
+            line["extras"]["incumbent"] = incumbent.measure(budget_s=150.0)
+        except Exception as e:
+            line["extras"]["incumbent"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -65,6 +65,12 @@ int tn_gemm_swiglu_bf16(const void* X, int64_t ldx, const void* Wg, const void* 
  * Segment sizes must be multiples of 256.  hf:models/llama/modeling_llama.py:251-289 (q_proj, k_proj, v_proj).
  * mode 0 with rope_cos/rope_sin ([M, 64] bf16 tables of tn_rope_table): the epilogue also applies RoPE to the q and k
  * segments (hf apply_rotary_pos_emb :151-168) with the rounding points of the unfused bf16 ops (bit-identical). */
+/* Down-proj dgrad fused with the SwiGLU backward (hf LlamaMLP.forward modeling_llama.py:182-184, backward of
+ * `down(silu(gate) * up)`): dH = dY[M,K] . W[K,N] (W = down_proj.weight, [d, ffn] row-major) never leaves the chip -
+ * the epilogue turns the accumulator tile into dG = (dH*U)*silu'(G) and dU = dH*silu(G) with the rounding points of
+ * tn_gemm_bf16 + tn_swiglu_bwd_bf16 (bit-identical to that two-kernel path).  Needs M, N >= 256. */
+int tn_gemm_dswiglu_bf16(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* G, const void* U,
+                         int64_t ldgu, void* dG, void* dU, int64_t lddg, int M, int N, int K, tn_stream_t stream);
 int tn_gemm_qkv_bf16(int mode, const void* A, int64_t lda, const void* B0, const void* B1, const void* B2, int64_t ldb,
                      void* D0, void* D1, void* D2, int64_t ldd, int d_f32, int s0, int s1, int s2, int M, int N, int K,
                      const void* rope_cos, const void* rope_sin, tn_stream_t stream);

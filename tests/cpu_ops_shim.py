@@ -196,11 +196,12 @@ _NAMES = ["gemm", "gemm_swiglu", "swiglu_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "ro
 def install():
     """Patch touchnet_b200.ops in THIS process (call inside spawned gloo workers / under monkeypatch)."""
     saved = {n: getattr(ops, n) for n in _NAMES}
-    saved["_FUSE_QKV"], saved["_chk"] = ops._FUSE_QKV, ops._chk
+    saved["_FUSE_QKV"], saved["_chk"], saved["_FUSE_DSWIGLU"] = ops._FUSE_QKV, ops._chk, ops._FUSE_DSWIGLU
     g = globals()
     for n in _NAMES:
         setattr(ops, n, g[n])
     ops._FUSE_QKV = False                     # the segmented-QKV launches have no stand-in: three plain GEMMs
+    ops._FUSE_DSWIGLU = False                 # fused dgrad + SwiGLU backward: the two-op form it is bit-identical to
     ops._chk = lambda *a, **k: None
     return saved
 

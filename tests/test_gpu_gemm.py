@@ -124,3 +124,25 @@ def test_fused_qkv_rope_epilogue_is_bit_identical_to_unfused(M, d, H, KV):
     ops.rope_apply_(plain[:, :nq], cos, sin, H, 128)
     ops.rope_apply_(plain[:, nq:nq + nkv], cos, sin, KV, 128)
     assert torch.equal(fused, plain)
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 1024, 256), (384, 520, 192), (8192, 14336, 4096)])
+def test_gemm_dswiglu_equals_dgrad_then_swiglu_backward(M, N, K):
+    """Down-proj dgrad with the SwiGLU backward in its epilogue == tn_gemm_bf16 (dH, bf16) followed by tn_swiglu_bwd_bf16,
+    bit for bit (same rounding points), incl. ragged edges and the Llama-3-8B shape (8192, 14336, 4096)."""
+    dev = require_cuda()
+    torch.manual_seed(M + N + K)
+    dy = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    wd = (torch.randn(K, N, device=dev) * 0.05).bfloat16()          # down_proj.weight [d, ffn]
+    g = torch.randn(M, N, device=dev).bfloat16()
+    u = torch.randn(M, N, device=dev).bfloat16()
+    dg_ref, du_ref = ops.swiglu_bwd(g, u, ops.gemm(dy, wd, b_mn=True))
+    dg, du = ops.gemm_dswiglu(dy, wd, g, u)
+    assert torch.equal(dg, dg_ref) and torch.equal(du, du_ref)
+    # and against fp32 math: dG = dH * u * silu'(g), dU = dH * silu(g)
+    dh = dy.float() @ wd.float()
+    sig = torch.sigmoid(g.float())
+    du32 = dh * (g.float() * sig)
+    dg32 = dh * u.float() * (sig * (1 + g.float() * (1 - sig)))
+    assert float((du.float() - du32).abs().max()) <= 2e-2 * float(du32.abs().max()) + 1e-2
+    assert float((dg.float() - dg32).abs().max()) <= 2e-2 * float(dg32.abs().max()) + 1e-2

@@ -304,7 +304,7 @@ def _cp_fsdp_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def _fsdp_peer_worker(rank, world, port, q):
+def _fsdp_peer_worker(rank, world, port, mode, q):
     """FSDP2=2 with touchnet_b200.fsdp_comm's peer-memory collectives plugged into every module group: the Comm
     protocol (allocate / call), barrier placement and buffer ring against the unsharded model.  Symmetric memory ->
     /dev/shm files, the two pull kernels -> torch on the mapped buffers."""
@@ -353,7 +353,7 @@ def _fsdp_peer_worker(rank, world, port, q):
             fully_shard(layer, mesh=mesh, mp_policy=mp_policy)
         fully_shard(model, mesh=mesh, mp_policy=mp_policy)
         mem = FilePeerMemory(mesh.get_group(), "cpu")
-        pool = fsdp_comm.install(model, mesh.get_group(), "cpu", mem=mem)
+        pool = fsdp_comm.install(model, mesh.get_group(), "cpu", mem=mem, mode=mode)
         row = slice(rank, rank + 1)
         worst, worst_name, err_fwd = 0.0, "", 0.0
         for step in range(2):                                             # second step reuses the ring buffers
@@ -366,7 +366,8 @@ def _fsdp_peer_worker(rank, world, port, q):
                 e = _rel(p.grad.full_tensor().float() * world, ref_grads[n].float())
                 if e > worst:
                     worst, worst_name = e, n
-        assert calls["rs"] == 2 * 3 and calls["ag"] >= 2 * 3, calls      # 2 blocks + root, every step
+        assert calls["rs"] == 2 * 3, calls                                # 2 blocks + root, every step
+        assert calls["ag"] >= 2 * 3 if mode == "pull" else calls["ag"] == 0, calls   # push mode: copies only, no gather kernel
         assert all(len(r) <= fsdp_comm.RING for r in pool._rings.values())
         mem.cleanup()
         q.put((rank, err_fwd, worst, worst_name))
@@ -443,7 +444,9 @@ def test_context_parallel_composes_with_fsdp2():
         assert worst < 3e-2, (rank, name, worst)
 
 
-def test_fsdp2_peer_memory_collectives_match_unsharded():
-    for rank, err_fwd, worst, name in _run(_fsdp_peer_worker, (), 30660):
+@pytest.mark.parametrize("mode", ["pull", "push"])
+def test_fsdp2_peer_memory_collectives_match_unsharded(mode):
+    """pull: tn_peer_* kernels read the peers' buffers; push: copy-engine pushes into the peers' buffers + local reduce."""
+    for rank, err_fwd, worst, name in _run(_fsdp_peer_worker, (mode,), 30660 if mode == "pull" else 30700):
         assert err_fwd < 2e-2, (rank, err_fwd)
         assert worst < 3e-2, (rank, name, worst)

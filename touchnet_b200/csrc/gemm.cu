@@ -430,6 +430,25 @@ extern "C" int tn_gemm_swiglu_bf16(const void* X, int64_t ldx, const void* Wg, c
   return launch_gemm<BN, false, false, 1>(tmA, tmG, tmU, p, stream);
 }
 
+namespace tn {
+int gemm_pair_dswiglu_dispatch(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* G, const void* U,
+                               int64_t ldgu, void* dG, void* dU, int64_t lddg, int M, int N, int K, cudaStream_t stream);
+}
+
+extern "C" int tn_gemm_dswiglu_bf16(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* G, const void* U,
+                                    int64_t ldgu, void* dG, void* dU, int64_t lddg, int M, int N, int K,
+                                    tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(dY && W && G && U && dG && dU, "tn_gemm_dswiglu_bf16: null pointer");
+  TN_REQUIRE(M >= 256 && N >= 256 && K > 0, "tn_gemm_dswiglu_bf16: needs M, N >= 256 (use tn_gemm_bf16 + tn_swiglu_bwd_bf16 below that)");
+  TN_REQUIRE(lddy % 8 == 0 && ldw % 8 == 0 && ldgu % 8 == 0 && lddg % 8 == 0 && N % 8 == 0,
+             "tn_gemm_dswiglu_bf16: leading dims and N must be multiples of 8");
+  TN_REQUIRE(((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(dG) |
+               reinterpret_cast<uintptr_t>(dU)) & 15) == 0, "tn_gemm_dswiglu_bf16: G, U, dG, dU must be 16 B aligned");
+  return gemm_pair_dswiglu_dispatch(dY, lddy, W, ldw, G, U, ldgu, dG, dU, lddg, M, N, K, stream);
+}
+
 extern "C" int tn_gemm_qkv_bf16(int mode, const void* A, int64_t lda, const void* B0, const void* B1, const void* B2,
                                 int64_t ldb, void* D0, void* D1, void* D2, int64_t ldd, int d_f32, int s0, int s1, int s2,
                                 int M, int N, int K, const void* rope_cos, const void* rope_sin, tn_stream_t stream_) {

@@ -52,6 +52,11 @@ struct PairParams {
   const bf16* rope_cos;
   const bf16* rope_sin;
   int rope_end;
+  // EPI 3 (down-proj dgrad fused with the SwiGLU backward, hf LlamaMLP.forward modeling_llama.py:182-184): the accumulator
+  // tile is dH; the epilogue reads the matching G / U tiles ([M, N] bf16, row stride ld_gu) and stores dG (tmD), dU (tmD2)
+  const bf16* aux_g;
+  const bf16* aux_u;
+  int64_t ld_gu;
 };
 
 __device__ __forceinline__ void pair_decode_tile(int tile, int num_m, int num_n, int group, int& m_blk, int& n_blk) {
@@ -66,7 +71,9 @@ __device__ __forceinline__ void pair_decode_tile(int tile, int num_m, int num_n,
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// EPI: 0 = bf16 D = acc (+R);  1 = SwiGLU (cols [0,128) gate, [128,256) up -> G,U,H);  2 = fp32 D = acc (+R)
+// EPI: 0 = bf16 D = acc (+R);  1 = SwiGLU (cols [0,128) gate, [128,256) up -> G,U,H);  2 = fp32 D = acc (+R);
+//      3 = SwiGLU backward on the dH accumulator: dG = (dH*U) * silu'(G), dU = dH * silu(G)  (same rounding points as
+//          tn_swiglu_bwd_bf16 applied to the bf16-rounded dH, so the fused and the two-kernel paths agree bit for bit)
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -254,7 +261,64 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         constexpr int CW = (EPI == 2) ? 32 : 64;   // columns per staging round (128 B per row)
         const int n0 = n_blk * P_BN;
-        if (EPI == 0 && p.rope_cos != nullptr && n0 < p.rope_end) {
+        if (EPI == 3) {
+          const bool row_ok = row < p.M;
+          const bf16* grow = p.aux_g + int64_t(row) * p.ld_gu;
+          const bf16* urow = p.aux_u + int64_t(row) * p.ld_gu;
+#pragma unroll 1
+          for (int c = 0; c < P_BN; c += 64) {
+            if (n_issued > 0) {
+              if (etid == 0) tma_store_wait_read<0>();
+              named_bar(2, 128);
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t v[32];
+              tmem_ld32(t_row + c + half * 32, v);
+              uint4 g4[4], u4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {                       // this row's G / U values of the 32 columns: issued with the TMEM read
+                const int col = n0 + c + half * 32 + q * 8;
+                const bool ok = row_ok && col < p.N;
+                g4[q] = ok ? *reinterpret_cast<const uint4*>(grow + col) : make_uint4(0, 0, 0, 0);
+                u4[q] = ok ? *reinterpret_cast<const uint4*>(urow + col) : make_uint4(0, 0, 0, 0);
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t gw[4] = {g4[q].x, g4[q].y, g4[q].z, g4[q].w}, uw[4] = {u4[q].x, u4[q].y, u4[q].z, u4[q].w};
+                uint32_t og[4], ou[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float rg[2], ru[2];
+#pragma unroll
+                  for (int e = 0; e < 2; ++e) {
+                    const float g = e ? bf16hi(gw[j]) : bf16lo(gw[j]);
+                    const float u = e ? bf16hi(uw[j]) : bf16lo(uw[j]);
+                    const float dh = bf16_round(__uint_as_float(v[q * 8 + j * 2 + e]));   // the bf16 dH the unfused path stores
+                    const float sig = 1.f / (1.f + __expf(-g));
+                    const float silu = g * sig;
+                    ru[e] = dh * bf16_round(silu);
+                    rg[e] = bf16_round(dh * u) * (sig * (1.f + g * (1.f - sig)));
+                  }
+                  og[j] = pack_bf16x2(rg[0], rg[1]);
+                  ou[j] = pack_bf16x2(ru[0], ru[1]);
+                }
+                const uint32_t off = r * 128u + ((uint32_t(half * 4 + q) ^ (r & 7u)) << 4);
+                *reinterpret_cast<uint4*>(sStg + off) = make_uint4(og[0], og[1], og[2], og[3]);
+                *reinterpret_cast<uint4*>(sStg + P_STG_BYTES + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+              }
+            }
+            fence_proxy_async_smem();
+            named_bar(2, 128);
+            if (etid == 0) {
+              tma_store_2d(&tmD, sStg, n0 + c, row0);                    // dG
+              tma_store_2d(&tmD2, sStg + P_STG_BYTES, n0 + c, row0);     // dU
+              tma_store_commit();
+            }
+            n_issued += 2;
+          }
+        } else if (EPI == 0 && p.rope_cos != nullptr && n0 < p.rope_end) {
           // ---- RoPE tile: 2 heads of 128 columns; pairs (j, j+64) sit in this thread's row ----
           const bool row_ok = row < p.M;
 #pragma unroll 1
@@ -458,6 +522,26 @@ int gemm_pair_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int6
   if (!a_mn && b_mn) return TN_PAIR(false, true);
   return TN_PAIR(true, true);
 #undef TN_PAIR
+}
+
+// Down-proj dgrad with the SwiGLU backward in its epilogue: dH = dY[M,K].W[K,N] (W = down_proj.weight [d, ffn], MN-major B),
+// dG / dU [M,N] from the accumulator and the saved G / U.  Caller guarantees M, N >= 256 (gemm.cu falls back otherwise).
+int gemm_pair_dswiglu_dispatch(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* G, const void* U,
+                               int64_t ldgu, void* dG, void* dU, int64_t lddg, int M, int N, int K, cudaStream_t stream) {
+  PairParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
+  p.group = gemm_group();
+  p.hint_a = gemm_l2_hints() ? kEvictLast : kEvictNormal;
+  p.hint_b = gemm_l2_hints() ? kEvictFirst : kEvictNormal;
+  p.aux_g = static_cast<const bf16*>(G); p.aux_u = static_cast<const bf16*>(U); p.ld_gu = ldgu;
+  CUtensorMap tmA, tmB, tmD, tmD2;
+  int rc;
+  if ((rc = encode_tmap_2d(&tmA, dY, 2, uint64_t(K), uint64_t(M), uint64_t(lddy) * 2, 64, P_BM, true))) return rc;
+  if ((rc = encode_tmap_2d(&tmB, W, 2, uint64_t(N), uint64_t(K), uint64_t(ldw) * 2, 64, 64, true))) return rc;
+  if ((rc = encode_tmap_2d(&tmD, dG, 2, uint64_t(N), uint64_t(M), uint64_t(lddg) * 2, 64, 128, true))) return rc;
+  if ((rc = encode_tmap_2d(&tmD2, dU, 2, uint64_t(N), uint64_t(M), uint64_t(lddg) * 2, 64, 128, true))) return rc;
+  return launch_pair<false, true, 3>(tmA, tmB, tmB, tmB, tmD, tmD2, tmD, p, stream);
 }
 
 // Three weights / gradients treated as one operand (see PairParams).  mode: 0 = forward  D[M, n0+n1+n2] = A·[B0;B1;B2]ᵀ

@@ -47,6 +47,15 @@ def _launch_all_gather(ptrs: list, bytes_each: int, out: torch.Tensor, max_ctas:
               torch.cuda.current_stream().cuda_stream)
 
 
+def _barrier(mem, channel: int) -> None:
+    """all-gather barriers on signal-pad channel 0, reduce-scatter barriers on channel 1: FSDP2 runs the two on different
+    streams and they overlap in backward (prefetched all-gather of block i-1 next to the reduce-scatter of block i)."""
+    try:
+        mem.barrier(channel)
+    except TypeError:            # test doubles without channels
+        mem.barrier()
+
+
 class _PeerPool:
     """Symmetric communication buffers of one process group, handed out FSDP2-style through `allocate`."""
 
@@ -104,7 +113,7 @@ class PeerReduceScatter(ReduceScatter):
         else:
             raise _lib.TouchNetB200Error(f"PeerReduceScatter: unsupported reduce op {op}")
         views = pool.views_of(input_tensor)
-        pool.mem.barrier()                                       # every rank's copy-in of this group has completed
+        _barrier(pool.mem, 1)                                    # every rank's copy-in of this group has completed
         _launch_reduce_scatter([v.data_ptr() for v in views], pool.rank * n, output_tensor, n, scale, self.max_ctas)
         return None                                              # stream-ordered on the caller's (reduce-scatter) stream
 
@@ -128,21 +137,102 @@ class PeerAllGather(AllGather):
         views = pool.views_of(output_tensor)
         if input_tensor.data_ptr() != output_tensor.data_ptr() + pool.rank * n * es:
             output_tensor.view(-1)[pool.rank * n:(pool.rank + 1) * n].copy_(input_tensor.reshape(-1))
-        pool.mem.barrier()                                       # every rank's shard is in its own buffer
+        _barrier(pool.mem, 0)                                    # every rank's shard is in its own buffer
         ptrs = [views[p].data_ptr() + p * n * es for p in range(pool.size)]
         _launch_all_gather(ptrs, n * es, output_tensor, self.max_ctas)
         return None
 
 
+class PushAllGather(AllGather):
+    """Parameter all-gather as COPY-ENGINE pushes: every rank writes its shard into every peer's (symmetric) output buffer
+    with plain device-to-device copies over NVLink - no SM is involved, so the tensor-core kernels the gather overlaps
+    with keep the whole chip (measured at N=2: NCCL's ring kernels slow the GEMMs they share the SMs / L2 with by 14 %;
+    the pull kernels above were slower still, profiles/README.md) - then one device-side barrier."""
+
+    def __init__(self, pool: _PeerPool):
+        self.pool = pool
+
+    def allocate(self, size, *, dtype, device) -> torch.Tensor:
+        return self.pool.allocate(size, dtype=dtype, device=device)
+
+    def __call__(self, output_tensor, input_tensor, group, async_op: bool = False):
+        pool = self.pool
+        n = input_tensor.numel()
+        if output_tensor.numel() != n * pool.size:
+            raise _lib.TouchNetB200Error("all-gather output must be world_size x input")
+        views = pool.views_of(output_tensor)
+        src = input_tensor.reshape(-1)
+        in_place = input_tensor.data_ptr() == output_tensor.data_ptr() + pool.rank * n * input_tensor.element_size()
+        for k in range(pool.size):                       # start with the next rank: the pushes of different ranks fan out
+            p = (pool.rank + 1 + k) % pool.size
+            if p == pool.rank and in_place:
+                continue
+            views[p].view(-1)[pool.rank * n:(pool.rank + 1) * n].copy_(src, non_blocking=True)
+        _barrier(pool.mem, 0)                            # every rank's pushes into this buffer have landed
+        return None
+
+
+class PushReduceScatter(ReduceScatter):
+    """fp32 gradient reduce-scatter: copy-engine pushes of every peer's chunk into that peer's receive slots, one barrier,
+    then ONE local kernel adds the world_size chunks in rank order (deterministic; tn_peer_reduce_scatter_f32 on local
+    pointers: HBM-bound, a few CTAs)."""
+
+    def __init__(self, pool: _PeerPool, max_ctas: int = 32):
+        self.pool, self.max_ctas = pool, max_ctas
+        self._recv: dict = {}       # numel -> ring of per-rank receive buffers [world * shard] fp32
+        self._next: dict = {}
+
+    def allocate(self, size, *, dtype, device) -> torch.Tensor:
+        return torch.empty(*[int(s) for s in size], dtype=dtype, device=device)     # peers never read the input buffer
+
+    def _slot(self, numel: int):
+        ring = self._recv.setdefault(numel, [])
+        i = self._next.get(numel, 0)
+        if i >= len(ring):
+            ring.append(self.pool.mem.alloc((numel,), torch.float32))                # collective, same order on all ranks
+        self._next[numel] = (i + 1) % RING
+        return ring[i]
+
+    def __call__(self, output_tensor, input_tensor, group, op, async_op: bool = False):
+        if input_tensor.dtype != torch.float32:
+            raise _lib.TouchNetB200Error("PushReduceScatter handles fp32 gradients (reduce_dtype=float32, the reference's default)")
+        pool = self.pool
+        n = output_tensor.numel()
+        if input_tensor.numel() != n * pool.size:
+            raise _lib.TouchNetB200Error("reduce-scatter input must be world_size x output")
+        if op == dist.ReduceOp.AVG:
+            scale = 1.0 / pool.size
+        elif op == dist.ReduceOp.SUM:
+            scale = 1.0
+        else:
+            raise _lib.TouchNetB200Error(f"PushReduceScatter: unsupported reduce op {op}")
+        recv = self._slot(n * pool.size)
+        flat = input_tensor.reshape(-1)
+        for k in range(1, pool.size):
+            p = (pool.rank + k) % pool.size
+            recv[p].view(-1)[pool.rank * n:(pool.rank + 1) * n].copy_(flat[p * n:(p + 1) * n], non_blocking=True)
+        _barrier(pool.mem, 1)                            # every peer's chunk for this rank has landed in recv[rank]
+        mine = recv[pool.rank]
+        ptrs = [(flat.data_ptr() + pool.rank * n * 4) if q == pool.rank else (mine.data_ptr() + q * n * 4)
+                for q in range(pool.size)]
+        _launch_reduce_scatter(ptrs, 0, output_tensor, n, scale, self.max_ctas)
+        return None
+
+
 def install(model: torch.nn.Module, group: dist.ProcessGroup, device, mem=None, all_gather: bool = True,
-            reduce_scatter: bool = True, max_ctas: int = 32) -> _PeerPool:
-    """Give every FSDP2 module group of `model` the peer-memory collectives (call after `fully_shard`)."""
+            reduce_scatter: bool = True, max_ctas: int = 32, mode: str = "pull") -> _PeerPool:
+    """Give every FSDP2 module group of `model` the peer-memory collectives (call after `fully_shard`).
+    mode "pull": tn_peer_* kernels read the peers' buffers; mode "push": copy-engine pushes + a local reduce kernel."""
     from torch.distributed.fsdp import FSDPModule
+    if mode not in ("pull", "push"):
+        raise ValueError(f"fsdp_comm.install: unknown mode {mode!r}")
     pool = _PeerPool(group, device, mem)
+    rs = (PeerReduceScatter if mode == "pull" else PushReduceScatter)(pool, max_ctas)
+    ag = PeerAllGather(pool, max_ctas) if mode == "pull" else PushAllGather(pool)
     for m in model.modules():
         if isinstance(m, FSDPModule):
             if reduce_scatter:
-                m.set_custom_reduce_scatter(PeerReduceScatter(pool, max_ctas))
+                m.set_custom_reduce_scatter(rs)
             if all_gather:
-                m.set_custom_all_gather(PeerAllGather(pool, max_ctas))
+                m.set_custom_all_gather(ag)
     return pool

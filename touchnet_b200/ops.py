@@ -237,6 +237,24 @@ def gemm_qkv_wgrad(dqkv, x, f32: bool, nq: int | None = None, nkv: int | None = 
     return outs
 
 
+_FUSE_DSWIGLU = os.environ.get("TN_FUSED_DSWIGLU", "1") != "0"   # A/B switch for measurements
+
+
+def gemm_dswiglu(dy: torch.Tensor, wd: torch.Tensor, g: torch.Tensor, u: torch.Tensor):
+    """(dG, dU) of hm = silu(g)*u given dy = d(hm . Wd^T): the down-proj dgrad GEMM dH = dy . Wd with the SwiGLU backward
+    in its epilogue (dH never written).  Falls back to the two-kernel path for shapes below one CTA-pair tile."""
+    M, K = dy.shape
+    N = wd.shape[1]
+    if not (_FUSE_DSWIGLU and M >= 256 and N >= 256 and N % 8 == 0 and g.stride(0) == u.stride(0)):
+        return swiglu_bwd(g, u, gemm(dy, wd, b_mn=True))
+    dg = torch.empty_like(g)
+    du = torch.empty_like(u)
+    assert dg.stride(0) == du.stride(0)
+    _lib.call("tn_gemm_dswiglu_bf16", dy.data_ptr(), dy.stride(0), wd.data_ptr(), wd.stride(0), g.data_ptr(), u.data_ptr(),
+              g.stride(0), dg.data_ptr(), du.data_ptr(), dg.stride(0), M, N, K, _st())
+    return dg, du
+
+
 def swiglu_bwd(g, u, dh, dg_out=None, du_out=None):
     M, N = g.shape
     dg = torch.empty_like(g) if dg_out is None else dg_out
@@ -574,11 +592,9 @@ class DecoderLayerFn(torch.autograd.Function):
             d2 = d2.to(BF16)
         # ---- MLP ----
         d2f = d2 if tp is None else tp.gather_rows(d2)     # backward of the forward reduce-scatter
-        dhm = gemm(d2f, wdb, b_mn=True)
+        dg, du = gemm_dswiglu(d2f, wdb, g, u)          # down-proj dgrad, SwiGLU backward in its epilogue
         dwd = _wgrad(d2f, hm, f32)
         del d2f
-        dg, du = swiglu_bwd(g, u, dhm)
-        del dhm
         dh2 = gemm(dg, wgb, b_mn=True)
         dh2 = gemm(du, wub, b_mn=True, residual=dh2, out=dh2)
         dwg = _wgrad(dg, h2, f32)

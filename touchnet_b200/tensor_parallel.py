@@ -267,9 +267,11 @@ class SymmPeerMemory:
         self._handles.append((t, h))
         return [h.get_buffer(r, tuple(shape), dtype) for r in range(self.size)]
 
-    def barrier(self) -> None:
-        """Device-side barrier on the current stream: stores issued before it by any rank are visible to all after it."""
-        self._handles[0][1].barrier()
+    def barrier(self, channel: int = 0) -> None:
+        """Device-side barrier on the current stream: stores issued before it by any rank are visible to all after it.
+        Collectives that may be in flight on different streams at the same time (FSDP2's all-gather and reduce-scatter
+        streams) must use different `channel`s of the signal pad."""
+        self._handles[0][1].barrier(channel=channel)
 
 
 class PeerTPContext(TPContext):

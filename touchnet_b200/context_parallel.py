@@ -114,8 +114,10 @@ def _reduce_scatter_seq(x: torch.Tensor, B: int, group, head_tail: bool = False)
 # 8(e): "halo exchange - an optimisation the reference does not do").  Same for dK/dV on the way back.  The exchanged
 # rows are whole 128-row blocks, so every block the kernels load is fully initialised.
 def _halo_enabled() -> bool:
+    """Default ON (validated on 2 x B200: same logits / gradients as the all-gather form, tools/check_cp.py, and faster);
+    TN_CP_HALO=0 selects the reference-style whole-shard K/V all-gather."""
     import os
-    return os.environ.get("TN_CP_HALO", "0") != "0"
+    return os.environ.get("TN_CP_HALO", "1") != "0"
 
 
 def halo_first_blocks(plan: ops.AttnPlan) -> list:

@@ -531,6 +531,7 @@ def main():
     sm_margin = int(os.environ.get("TN_SM_MARGIN", "0"))
     _lib.call("tn_set_sm_margin", sm_margin)   # leave SMs to the FSDP2 NCCL kernels so that they overlap the GEMMs
     _lib.call("tn_set_gemm_l2_hints", int(os.environ.get("TN_GEMM_L2_HINTS", "0") != "0"))   # A/B switch
+    _lib.call("tn_set_gemm_split_tail", int(os.environ.get("TN_GEMM_SPLIT_TAIL", "1") != "0"))   # A/B switch
     B, T = args.batch, args.seq_len
     cfg = asr_config(args.layers)
 
@@ -554,6 +555,8 @@ def main():
             os.environ.setdefault("TN_TP_PEER", "1")    # block collectives as GEMM epilogues storing into peer memory (validated
             from touchnet_b200 import tensor_parallel   # on 2 x B200, tools/check_tp.py); TN_TP_PEER=0 -> NCCL
             tensor_parallel.apply_tp(model, full_mesh["tp"])
+            # loss parallel (the reference recipes' setting, run.sh:140): vocabulary-sharded logits into the pack-loss
+            model.language_model.loss_parallel = os.environ.get("TN_TP_LOSS_PARALLEL", "1") != "0"
         if cp > 1:
             from touchnet_b200 import context_parallel
             context_parallel.enable_context_parallel(model, full_mesh["cp"].get_group())
@@ -580,7 +583,8 @@ def main():
             try:
                 from touchnet_b200 import fsdp_comm
                 fsdp_comm.install(model, mesh.get_group(), dev, max_ctas=int(os.environ.get("TN_FSDP_PEER_CTAS", "32")),
-                                  mode="push" if fsdp_mode == "push" else "pull")
+                                  mode="push" if fsdp_mode == "push" else "pull",
+                                  direct=os.environ.get("TN_FSDP_DIRECT", "1") != "0")
                 FSDP_COLLECTIVES = ("copy-engine pushes over NVLink symmetric memory + local reduce kernel" if fsdp_mode == "push"
                                     else "pull kernels over NVLink symmetric memory")
             except Exception as e:           # symmetric memory unavailable on this box: the reference's NCCL path

@@ -37,6 +37,7 @@ int tn_set_sm_margin(int sms);
 /* Tuning knob: raster group of the CTA-pair GEMM = number of 256-row M blocks whose tiles are walked across all N blocks
  * before moving on (default 8; decides which operand strips stay L2-resident between waves).  Results do not depend on it. */
 int tn_set_gemm_group(int m_blocks);
+int tn_set_gemm_split_tail(int on);  /* 1 (default): a last wave that would leave over half of the CTA pairs idle runs as 256x128 half tiles */
 int tn_set_gemm_l2_hints(int on);   /* 1: A strips evict-last, B strips evict-first in the CTA-pair GEMM TMA loads (default 0: measured 6 % slower) */
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -190,6 +191,12 @@ int tn_pack_ce_fwd_bf16(const void* logits, int64_t ld, const int64_t* labels, f
                         int64_t M, int V, tn_stream_t stream);
 int tn_pack_ce_bwd_bf16(void* logits, int64_t ld, const int64_t* labels, const int64_t* sentence_lens, const float* lse,
                         const float* grad_scalar, float scale, int64_t M, int V, tn_stream_t stream);
+/* vocabulary-parallel backward (tensor-parallel lm_head with loss parallel, ref: touchnet/utils/distributed.py:322-323,
+ * touchnet/models/llama/parallelize_llama.py:127-131): `logits` holds columns [v0, v0+V_local) of a V_total-wide vocabulary,
+ * labels are GLOBAL ids, lse the GLOBAL logsumexp (all-reduced by the caller from per-shard tn_pack_ce_fwd_bf16 results). */
+int tn_pack_ce_bwd_vp_bf16(void* logits, int64_t ld, const int64_t* labels_global, const int64_t* sentence_lens,
+                           const float* lse_global, const float* grad_scalar, float scale, int64_t M, int V_local, int64_t v0,
+                           int64_t V_total, tn_stream_t stream);
 /* fwd and bwd (upstream gradient 1) of the above in ONE launch over a chunk of rows: the building block of the fused
  * lm_head + loss (touchnet_b200/loss.py::FusedLinearCEFn - the reference's best path is Liger's fused-linear-cross-entropy,
  * touchnet/bin/train.py:443-445, which never materialises [B,T,V] logits either).  IN PLACE like the bwd entry point. */
@@ -250,6 +257,10 @@ int tn_peer_reduce_scatter_f32(const void* const* inputs, int n_peers, int64_t s
                                float scale, int max_ctas, tn_stream_t stream);
 int tn_peer_all_gather(const void* const* inputs, int n_peers, int64_t bytes_each, void* out, int max_ctas,
                        tn_stream_t stream);
+/* out[i] = scale * sum_k float(inputs[k][i]): bf16 chunks (local memory), fp32 accumulation in input order - the reduce step
+ * of the direct-push reduce-scatter of touchnet_b200/fsdp_comm.py (same sum as FSDP2's fp32 reduce of bf16 gradients). */
+int tn_reduce_bf16_to_f32(const void* const* inputs, int n_inputs, float* out, int64_t numel, float scale, int max_ctas,
+                          tn_stream_t stream);
 
 #ifdef __cplusplus
 }

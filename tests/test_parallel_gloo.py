@@ -337,7 +337,16 @@ def _fsdp_peer_worker(rank, world, port, mode, q):
             for i, p in enumerate(ptrs):
                 o[i * bytes_each:(i + 1) * bytes_each] = at(p, bytes_each, torch.uint8)
 
+        def fake_rs16(ptrs, out, numel, scale, max_ctas):                  # tn_reduce_bf16_to_f32: bf16 chunks, fp32 sum
+            calls["rs"] += 1
+            calls["rs16"] = calls.get("rs16", 0) + 1
+            acc = at(ptrs[0], numel, torch.bfloat16).float()
+            for p in ptrs[1:]:
+                acc += at(p, numel, torch.bfloat16).float()
+            out.view(-1).copy_(acc * scale)
+
         fsdp_comm._launch_reduce_scatter, fsdp_comm._launch_all_gather = fake_rs, fake_ag
+        fsdp_comm._launch_reduce_bf16 = fake_rs16
         model, text = _build(False, False)
         B, T = 2, 256
         kw, doc, tgt = _inputs(B, T, text.vocab_size, False)
@@ -368,6 +377,8 @@ def _fsdp_peer_worker(rank, world, port, mode, q):
                     worst, worst_name = e, n
         assert calls["rs"] == 2 * 3, calls                                # 2 blocks + root, every step
         assert calls["ag"] >= 2 * 3 if mode == "pull" else calls["ag"] == 0, calls   # push mode: copies only, no gather kernel
+        if mode == "push":                                               # direct form: bf16 chunks straight from autograd's
+            assert calls.get("rs16", 0) == 2 * 3, calls                   # gradients, FSDP2's copy-in bypassed every time
         assert all(len(r) <= fsdp_comm.RING for r in pool._rings.values())
         mem.cleanup()
         q.put((rank, err_fwd, worst, worst_name))

@@ -59,7 +59,8 @@ fully_shard(model, mesh=mesh, mp_policy=mp)
 if os.environ.get("TN_FSDP_PEER", "0") != "0":                   # our pull kernels over NVLink peer memory instead of NCCL
     from touchnet_b200 import fsdp_comm
     fsdp_comm.install(model, mesh.get_group(), dev, max_ctas=int(os.environ.get("TN_FSDP_PEER_CTAS", "32")),
-                              mode="push" if os.environ["TN_FSDP_PEER"] == "push" else "pull")
+                              mode="push" if os.environ["TN_FSDP_PEER"] == "push" else "pull",
+                              direct=os.environ.get("TN_FSDP_DIRECT", "1") != "0")
     if rank == 0:
         print("FSDP2 collectives: tn_peer_reduce_scatter_f32 / tn_peer_all_gather over symmetric memory")
 loss = step(model, slice(rank, rank + 1))

@@ -23,6 +23,7 @@ _SIGNATURES = {
     "tn_set_sm_margin": [_i],
     "tn_set_gemm_group": [_i],
     "tn_set_gemm_l2_hints": [_i],
+    "tn_set_gemm_split_tail": [_i],
     "tn_gemm_bf16": [_vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _vp],
     "tn_gemm_swiglu_bf16": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _vp],
     "tn_gemm_dswiglu_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp],
@@ -48,9 +49,11 @@ _SIGNATURES = {
     "tn_bestrq_tokenize_f32": [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp, _vp],
     "tn_pack_ce_fwd_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _vp],
     "tn_pack_ce_bwd_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _f, _i64, _i, _vp],
+    "tn_pack_ce_bwd_vp_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _f, _i64, _i, _i64, _i64, _vp],
     "tn_pack_layout_i64": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "tn_peer_reduce_scatter_f32": [_vp, _i, _i64, _vp, _i64, _f, _i, _vp],
     "tn_peer_all_gather": [_vp, _i, _i64, _vp, _i, _vp],
+    "tn_reduce_bf16_to_f32": [_vp, _i, _vp, _i64, _f, _i, _vp],
     "tn_sumsq_num_partials": [],
     "tn_sumsq_f32": [_vp, _i64, _vp, _vp, _vp],
     "tn_scale_f32": [_vp, _i64, _vp, _vp],

@@ -62,6 +62,33 @@ __global__ void __launch_bounds__(COLL_THREADS) peer_reduce_scatter_kernel(const
     }
 }
 
+// bf16 inputs, fp32 sum: out[i] = scale * sum_p float(in_p[i]).  The reduce step of the direct-push reduce-scatter
+// (fsdp_comm.PushReduceScatter): every rank's bf16 gradient chunk for this rank already sits in a local receive slot
+// (copy-engine pushes), so this is one HBM-bound pass; fp32 accumulation in rank order = what casting every chunk to fp32
+// and reduce-scattering in fp32 (FSDP2's reduce_dtype=float32) computes.
+__global__ void __launch_bounds__(COLL_THREADS) reduce_bf16_to_f32_kernel(const PeerPtrs in, int n_peers,
+                                                                          float* __restrict__ out, int64_t numel,
+                                                                          float scale) {
+  const int64_t nvec = numel >> 3;
+  for (int64_t i = int64_t(blockIdx.x) * COLL_THREADS + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * COLL_THREADS) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < n_peers; ++k) {
+      const uint4 v = reinterpret_cast<const uint4*>(in.p[k])[i];
+      acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
+      acc[4] += bf16lo(v.z); acc[5] += bf16hi(v.z); acc[6] += bf16lo(v.w); acc[7] += bf16hi(v.w);
+    }
+    float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+    o[0] = make_float4(acc[0] * scale, acc[1] * scale, acc[2] * scale, acc[3] * scale);
+    o[1] = make_float4(acc[4] * scale, acc[5] * scale, acc[6] * scale, acc[7] * scale);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = nvec * 8 + threadIdx.x; i < numel; i += COLL_THREADS) {
+      float s = 0.f;
+      for (int k = 0; k < n_peers; ++k) s += __bfloat162float(static_cast<const bf16*>(in.p[k])[i]);
+      out[i] = s * scale;
+    }
+}
+
 __global__ void __launch_bounds__(COLL_THREADS) peer_all_gather_kernel(const PeerPtrs in, int n_peers, int64_t vec_each,
                                                                        uint4* __restrict__ out) {
   // blockIdx.y = source rank; 16-byte vectors
@@ -123,6 +150,29 @@ extern "C" int tn_peer_all_gather(const void* const* inputs, int n_peers, int64_
   if (gx < 1) gx = 1;
   peer_all_gather_kernel<<<dim3(unsigned(gx), unsigned(n_peers)), COLL_THREADS, 0, stream>>>(pp, n_peers, vec_each,
                                                                                            static_cast<uint4*>(out));
+  TN_CHECK_CUDA(cudaGetLastError());
+  return TN_OK;
+}
+
+extern "C" int tn_reduce_bf16_to_f32(const void* const* inputs, int n_inputs, float* out, int64_t numel, float scale,
+                                     int max_ctas, tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(inputs && out, "tn_reduce_bf16_to_f32: null pointer");
+  TN_REQUIRE(n_inputs >= 1 && n_inputs <= COLL_MAX_PEERS, "tn_reduce_bf16_to_f32: n_inputs=%d out of range", n_inputs);
+  PeerPtrs pp{};
+  for (int k = 0; k < n_inputs; ++k) {
+    TN_REQUIRE(inputs[k] && (reinterpret_cast<uintptr_t>(inputs[k]) & 15u) == 0,
+               "tn_reduce_bf16_to_f32: input %d null or not 16-byte aligned", k);
+    pp.p[k] = inputs[k];
+  }
+  TN_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, "tn_reduce_bf16_to_f32: out not 16-byte aligned");
+  if (numel == 0) return TN_OK;
+  int64_t grid = (numel / 8 + COLL_THREADS - 1) / COLL_THREADS;
+  const int cap = max_ctas > 0 ? max_ctas : 32;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  reduce_bf16_to_f32_kernel<<<unsigned(grid), COLL_THREADS, 0, stream>>>(pp, n_inputs, out, numel, scale);
   TN_CHECK_CUDA(cudaGetLastError());
   return TN_OK;
 }

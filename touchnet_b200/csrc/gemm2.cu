@@ -38,6 +38,7 @@ struct PairParams {
   // consumed within about one wave and not touched again until the next group -> A evict-last, B evict-first keeps the
   // strips that will be re-read resident in the 126 MB L2 (tn_set_gemm_l2_hints, default on)
   uint64_t hint_a, hint_b;
+  int split_tail;            // 1: half tiles in the last wave (pair_work); 0 for A/B runs (tn_set_gemm_split_tail)
   const void* R;
   int64_t ldr;
   // segmented operands: several weight tensors that are separate nn.Parameters (q/k/v projections) behave as one GEMM
@@ -67,6 +68,22 @@ __device__ __forceinline__ void pair_decode_tile(int tile, int num_m, int num_n,
   const int r = tile - g * per_group;
   m_blk = first_m + (r % gsize);
   n_blk = r / gsize;
+}
+
+// Work list of one launch: the tiles of all full waves, then - when the last wave would leave more than half of the
+// clusters idle - the remaining tiles as 256 x 128 HALF tiles (2x as many items, each half as long), so the tail costs
+// half a wave instead of a whole one (o_proj wgrad: 256 tiles on 74 clusters = 3.46 waves -> 3 + 0.5 instead of 4).
+// A half tile loads the same operand boxes (the B box of CTA r simply starts 64 rows later and only its first 64 rows
+// are used), issues N = 128 MMAs into the first 128 accumulator columns and stores 128 columns.
+struct PairWork { int tile; int half; };   // half: -1 = full tile, 0 / 1 = left / right 128 columns
+__device__ __forceinline__ int pair_num_work(int num_tiles, int C, bool allow) {
+  const int full_w = (num_tiles / C) * C, R = num_tiles - full_w;
+  return (allow && R > 0 && 2 * R <= C) ? full_w + 2 * R : num_tiles;
+}
+__device__ __forceinline__ PairWork pair_work(int w, int num_tiles, int C, bool allow) {
+  const int full_w = (num_tiles / C) * C, R = num_tiles - full_w;
+  if (!(allow && R > 0 && 2 * R <= C) || w < full_w) return PairWork{w, -1};
+  return PairWork{full_w + ((w - full_w) >> 1), (w - full_w) & 1};
 }
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -117,17 +134,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_tiles = p.num_m * p.num_n;
+  const bool split_ok = (EPI != 1) && p.split_tail != 0;
+  const int num_work = pair_num_work(num_tiles, num_clusters, split_ok);
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; transaction bytes counted on the leader's barrier) ============
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const PairWork wk = pair_work(w, num_tiles, num_clusters, split_ok);
         int m_blk, n_blk;
-        pair_decode_tile(tile, p.num_m, p.num_n, p.group, m_blk, n_blk);
+        pair_decode_tile(wk.tile, p.num_m, p.num_n, p.group, m_blk, n_blk);
         const int m0 = m_blk * 256 + int(rank) * P_BM;
-        int n0 = (EPI == 1) ? n_blk * 128 : n_blk * P_BN + int(rank) * (P_BN / 2);
+        int n0 = (EPI == 1) ? n_blk * 128
+                            : (wk.half < 0 ? n_blk * P_BN + int(rank) * (P_BN / 2)
+                                           : n_blk * P_BN + wk.half * (P_BN / 2) + int(rank) * (P_BN / 4));
         const CUtensorMap* bmap = &tmB;
         if (EPI != 1 && p.b_seg == 1) {   // weight segment that owns these 128 output columns
           const int sg = (n0 >= p.off1) + (n0 >= p.off2);
@@ -168,12 +190,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, P_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_full = make_idesc_bf16(256, P_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_half = make_idesc_bf16(256, P_BN / 2, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const uint32_t idesc = pair_work(w, num_tiles, num_clusters, split_ok).half < 0 ? idesc_full : idesc_half;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * P_BN);
@@ -206,9 +230,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t n_issued = 0;                       // staging rounds issued so far (buffer ring position)
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (int w = cluster_id; w < num_work; w += num_clusters) {
+      const PairWork wk = pair_work(w, num_tiles, num_clusters, split_ok);
       int m_blk, n_blk;
-      pair_decode_tile(tile, p.num_m, p.num_n, p.group, m_blk, n_blk);
+      pair_decode_tile(wk.tile, p.num_m, p.num_n, p.group, m_blk, n_blk);
+      const int ncols = wk.half < 0 ? P_BN : P_BN / 2;          // accumulator columns of this work item
       const int row0 = m_blk * 256 + int(rank) * P_BM;
       const int row = row0 + int(r);
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -260,13 +286,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else {
         constexpr int CW = (EPI == 2) ? 32 : 64;   // columns per staging round (128 B per row)
-        const int n0 = n_blk * P_BN;
+        const int n0 = n_blk * P_BN + (wk.half > 0 ? P_BN / 2 : 0);
         if (EPI == 3) {
           const bool row_ok = row < p.M;
           const bf16* grow = p.aux_g + int64_t(row) * p.ld_gu;
           const bf16* urow = p.aux_u + int64_t(row) * p.ld_gu;
 #pragma unroll 1
-          for (int c = 0; c < P_BN; c += 64) {
+          for (int c = 0; c < ncols; c += 64) {
             if (n_issued > 0) {
               if (etid == 0) tma_store_wait_read<0>();
               named_bar(2, 128);
@@ -322,7 +348,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // ---- RoPE tile: 2 heads of 128 columns; pairs (j, j+64) sit in this thread's row ----
           const bool row_ok = row < p.M;
 #pragma unroll 1
-          for (int head = 0; head < 2; ++head) {
+          for (int head = 0; head < ncols / 128; ++head) {
             if (n_issued > 0) {
               if (etid == 0) tma_store_wait_read<0>();
               named_bar(2, 128);
@@ -379,7 +405,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           drow0 = row0 - (sg == 0 ? 0 : (sg == 1 ? p.off1 : p.off2));
         }
 #pragma unroll 1
-        for (int c = 0; c < P_BN; c += CW) {
+        for (int c = 0; c < ncols; c += CW) {
           uint8_t* stg = sStg + (n_issued & 1u) * P_STG_BYTES;
           if (n_issued >= 2) {
             if (etid == 0) {
@@ -501,6 +527,7 @@ int gemm_pair_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int6
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
   p.group = gemm_group();
+  p.split_tail = gemm_split_tail();
   p.hint_a = gemm_l2_hints() ? kEvictLast : kEvictNormal;
   p.hint_b = gemm_l2_hints() ? kEvictFirst : kEvictNormal;
   p.R = R; p.ldr = ldr;
@@ -532,6 +559,7 @@ int gemm_pair_dswiglu_dispatch(const void* dY, int64_t lddy, const void* W, int6
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
   p.group = gemm_group();
+  p.split_tail = gemm_split_tail();
   p.hint_a = gemm_l2_hints() ? kEvictLast : kEvictNormal;
   p.hint_b = gemm_l2_hints() ? kEvictFirst : kEvictNormal;
   p.aux_g = static_cast<const bf16*>(G); p.aux_u = static_cast<const bf16*>(U); p.ld_gu = ldgu;
@@ -558,6 +586,7 @@ int gemm_pair_seg_dispatch(int mode, const void* A, int64_t lda, const void* con
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + P_BN - 1) / P_BN; p.num_k = (K + P_BK - 1) / P_BK;
   p.group = gemm_group();
+  p.split_tail = gemm_split_tail();
   p.hint_a = gemm_l2_hints() ? kEvictLast : kEvictNormal;
   p.hint_b = gemm_l2_hints() ? kEvictFirst : kEvictNormal;
   p.off1 = seg[0]; p.off2 = seg[0] + seg[1];
@@ -597,6 +626,7 @@ int gemm_pair_swiglu_dispatch(const void* X, int64_t ldx, const void* Wg, const 
   p.M = M; p.N = N; p.K = K;
   p.num_m = (M + 255) / 256; p.num_n = (N + 127) / 128; p.num_k = (K + P_BK - 1) / P_BK;
   p.group = gemm_group();
+  p.split_tail = gemm_split_tail();
   p.hint_a = gemm_l2_hints() ? kEvictLast : kEvictNormal;
   p.hint_b = gemm_l2_hints() ? kEvictFirst : kEvictNormal;
   CUtensorMap tmA, tmG, tmU, tmDG, tmDU, tmDH;

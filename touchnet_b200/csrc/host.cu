@@ -91,6 +91,8 @@ static int g_gemm_group = 8;
 
 int gemm_group() { return g_gemm_group; }
 void set_gemm_l2_hints(int on);
+static int g_gemm_split_tail = 1;
+int gemm_split_tail() { return g_gemm_split_tail; }
 static int g_gemm_l2_hints = 0;   // measured: evict-first on B costs 6 % (partner CTAs of a wave lose the strip), see profiles/README.md
 int gemm_l2_hints() { return g_gemm_l2_hints; }
 void set_gemm_l2_hints(int on) { g_gemm_l2_hints = on ? 1 : 0; }
@@ -123,6 +125,11 @@ int tn_set_sm_margin(int sms) {
 int tn_set_gemm_group(int m_blocks) {
   if (m_blocks < 1 || m_blocks > 64) return tn::fail(tn::TN_ERR_ARG, "tn_set_gemm_group: %d out of range [1,64]", m_blocks);
   tn::g_gemm_group = m_blocks;
+  return tn::TN_OK;
+}
+
+int tn_set_gemm_split_tail(int on) {
+  tn::g_gemm_split_tail = on ? 1 : 0;
   return tn::TN_OK;
 }
 

@@ -36,6 +36,7 @@ int encode_tmap_3d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t d
 
 int sm_count();
 int gemm_group();   // raster group of the CTA-pair GEMM (tn_set_gemm_group)
+int gemm_split_tail();  // 1: the CTA-pair GEMM turns a sparse last wave into half tiles (tn_set_gemm_split_tail)
 int gemm_l2_hints();  // 1: operand loads of the CTA-pair GEMM carry L2 eviction hints (tn_set_gemm_l2_hints)
 
 }  // namespace tn

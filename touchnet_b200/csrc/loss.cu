@@ -87,11 +87,15 @@ __global__ void __launch_bounds__(CE_THREADS) pack_ce_bwd_kernel(bf16* __restric
                                                                  const int64_t* __restrict__ sentence_lens,
                                                                  const float* __restrict__ lse_in,
                                                                  const float* __restrict__ grad_scalar, float scale,
-                                                                 int64_t M, int V) {
+                                                                 int64_t M, int V, int64_t v0, int64_t v_total) {
+  // vocabulary-parallel form (tensor parallel lm_head, ref loss_parallel: touchnet/utils/distributed.py:322-323): this tensor
+  // holds columns [v0, v0 + V) of a v_total-wide vocabulary, labels are global ids, lse is the GLOBAL logsumexp; a row is
+  // valid iff its label is in [0, v_total), the one-hot lands here only if the label is one of OUR columns
   const int64_t row = blockIdx.x;
   bf16* x = logits + row * ld;
-  const int64_t lab = labels[row];
-  const bool valid = lab >= 0 && lab < V;
+  const int64_t lab_g = labels[row];
+  const bool valid = lab_g >= 0 && lab_g < v_total;
+  const int64_t lab = lab_g - v0;              // local column of the label (outside [0, V): another rank's column)
   const float g = grad_scalar ? grad_scalar[0] : 1.f;
   const float w = valid ? scale * g / float(sentence_lens ? sentence_lens[row] : 1) : 0.f;
   const float lse = lse_in[row];
@@ -227,7 +231,22 @@ extern "C" int tn_pack_ce_bwd_bf16(void* logits, int64_t ld, const int64_t* labe
   TN_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0, "tn_pack_ce_bwd_bf16: logits rows must be 16 B aligned");
   if (M == 0) return TN_OK;
   pack_ce_bwd_kernel<<<unsigned(M), CE_THREADS, 0, stream>>>(static_cast<bf16*>(logits), ld, labels, sentence_lens, lse,
-                                                             grad_scalar, scale, M, V);
+                                                             grad_scalar, scale, M, V, 0, V);
+  TN_CHECK_CUDA(cudaGetLastError());
+  return TN_OK;
+}
+
+extern "C" int tn_pack_ce_bwd_vp_bf16(void* logits, int64_t ld, const int64_t* labels_global, const int64_t* sentence_lens,
+                                      const float* lse_global, const float* grad_scalar, float scale, int64_t M, int V_local,
+                                      int64_t v0, int64_t V_total, tn_stream_t stream_) {
+  clear_error();
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(logits && labels_global && lse_global, "tn_pack_ce_bwd_vp_bf16: null pointer");
+  TN_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0, "tn_pack_ce_bwd_vp_bf16: logits rows must be 16 B aligned");
+  TN_REQUIRE(v0 >= 0 && v0 + V_local <= V_total, "tn_pack_ce_bwd_vp_bf16: column range outside the vocabulary");
+  if (M == 0) return TN_OK;
+  pack_ce_bwd_kernel<<<unsigned(M), CE_THREADS, 0, stream>>>(static_cast<bf16*>(logits), ld, labels_global, sentence_lens,
+                                                             lse_global, grad_scalar, scale, M, V_local, v0, V_total);
   TN_CHECK_CUDA(cudaGetLastError());
   return TN_OK;
 }

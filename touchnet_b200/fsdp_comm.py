@@ -47,6 +47,45 @@ def _launch_all_gather(ptrs: list, bytes_each: int, out: torch.Tensor, max_ctas:
               torch.cuda.current_stream().cuda_stream)
 
 
+def _launch_reduce_bf16(ptrs: list, out: torch.Tensor, numel: int, scale: float, max_ctas: int) -> None:
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    _lib.call("tn_reduce_bf16_to_f32", arr, len(ptrs), out.data_ptr(), numel, float(scale), max_ctas,
+              torch.cuda.current_stream().cuda_stream)
+
+
+# ---- FSDP2's reduce-scatter copy-in, bypassed for the direct-push reduce-scatter -------------------------------------------
+# torch.distributed.fsdp._fully_shard._fsdp_collectives.foreach_reduce copies (and casts) every unsharded gradient into one
+# [world, shard] buffer with a chunk_cat kernel ON THE COMPUTE STREAM (26 ms of a 407 ms step at N=2) before it calls the
+# reduce-scatter.  A chunk of a dim-0-sharded gradient is contiguous, so the direct form needs no staging at all: the
+# reduce-scatter pushes each chunk from where autograd left it.  The hook below stands in for the copy-in when (and only
+# when) the buffer belongs to an installed PushReduceScatter and every gradient qualifies; anything else takes torch's path.
+_DIRECT: list = []          # installed PushReduceScatter objects
+_orig_copy_in = None
+
+
+def _copy_in_hook(unsharded_grads, reduce_scatter_input, world_size):
+    ptr = reduce_scatter_input.data_ptr()
+    for comm in _DIRECT:
+        if comm._expect_input == ptr and comm.can_direct(unsharded_grads, world_size):
+            comm._stash = (ptr, list(unsharded_grads))       # keeps the gradients alive until their pushes are enqueued
+            return
+    return _orig_copy_in(unsharded_grads, reduce_scatter_input, world_size)
+
+
+def _patch_copy_in() -> bool:
+    global _orig_copy_in
+    if _orig_copy_in is not None:
+        return True
+    try:
+        from torch.distributed.fsdp._fully_shard import _fsdp_collectives as fc
+        _orig_copy_in = fc.foreach_reduce_scatter_copy_in
+        fc.foreach_reduce_scatter_copy_in = _copy_in_hook
+        return True
+    except Exception:        # a torch without this seam: the staged path (copy-in + push of the staged chunks) still works
+        _orig_copy_in = None
+        return False
+
+
 def _barrier(mem, channel: int) -> None:
     """all-gather barriers on signal-pad channel 0, reduce-scatter barriers on channel 1: FSDP2 runs the two on different
     streams and they overlap in backward (prefetched all-gather of block i-1 next to the reduce-scatter of block i)."""
@@ -173,29 +212,52 @@ class PushAllGather(AllGather):
 
 
 class PushReduceScatter(ReduceScatter):
-    """fp32 gradient reduce-scatter: copy-engine pushes of every peer's chunk into that peer's receive slots, one barrier,
-    then ONE local kernel adds the world_size chunks in rank order (deterministic; tn_peer_reduce_scatter_f32 on local
-    pointers: HBM-bound, a few CTAs)."""
+    """Gradient reduce-scatter (fp32 result): copy-engine pushes of every peer's chunk into that peer's receive slots, one
+    barrier, then ONE local kernel adds the world_size chunks in rank order (deterministic, HBM-bound, a few CTAs).
 
-    def __init__(self, pool: _PeerPool, max_ctas: int = 32):
+    Direct form (default when FSDP2's copy-in seam can be patched, `direct=True`): the chunks are pushed straight from the
+    unsharded gradients autograd produced - bf16 under the reference's mixed-precision policy, so half the NVLink bytes -
+    and summed in fp32 by tn_reduce_bf16_to_f32; FSDP2's chunk_cat copy-in (a kernel on the compute stream) is skipped.
+    Staged form: FSDP2 copies into the [world, shard] input buffer as usual and the chunks are pushed from there."""
+
+    def __init__(self, pool: _PeerPool, max_ctas: int = 32, direct: bool = True):
         self.pool, self.max_ctas = pool, max_ctas
-        self._recv: dict = {}       # numel -> ring of per-rank receive buffers [world * shard] fp32
+        self._recv: dict = {}       # (numel, dtype) -> ring of per-rank receive buffers [world * shard]
         self._next: dict = {}
+        self._expect_input = None   # data_ptr of the reduce-scatter input buffer handed out last
+        self._stash = None          # (input data_ptr, unsharded gradients) left by the copy-in hook
+        self.direct = bool(direct) and _patch_copy_in()
+        if self.direct:
+            _DIRECT.append(self)
 
     def allocate(self, size, *, dtype, device) -> torch.Tensor:
-        return torch.empty(*[int(s) for s in size], dtype=dtype, device=device)     # peers never read the input buffer
+        t = torch.empty(*[int(s) for s in size], dtype=dtype, device=device)        # peers never read this buffer
+        self._expect_input = t.data_ptr()
+        return t
 
-    def _slot(self, numel: int):
-        ring = self._recv.setdefault(numel, [])
-        i = self._next.get(numel, 0)
+    def can_direct(self, grads, world_size: int) -> bool:
+        if world_size != self.pool.size or not grads:
+            return False
+        dt = grads[0].dtype
+        if dt not in (torch.bfloat16, torch.float32):
+            return False
+        for g in grads:
+            if g.dtype != dt or not g.is_contiguous() or g.dim() == 0 or g.shape[0] % world_size != 0:
+                return False
+            if (g.numel() // world_size * g.element_size()) % 16 != 0:
+                return False
+        return True
+
+    def _slot(self, numel: int, dtype):
+        key = (numel, dtype)
+        ring = self._recv.setdefault(key, [])
+        i = self._next.get(key, 0)
         if i >= len(ring):
-            ring.append(self.pool.mem.alloc((numel,), torch.float32))                # collective, same order on all ranks
-        self._next[numel] = (i + 1) % RING
+            ring.append(self.pool.mem.alloc((numel,), dtype))                        # collective, same order on all ranks
+        self._next[key] = (i + 1) % RING
         return ring[i]
 
     def __call__(self, output_tensor, input_tensor, group, op, async_op: bool = False):
-        if input_tensor.dtype != torch.float32:
-            raise _lib.TouchNetB200Error("PushReduceScatter handles fp32 gradients (reduce_dtype=float32, the reference's default)")
         pool = self.pool
         n = output_tensor.numel()
         if input_tensor.numel() != n * pool.size:
@@ -206,7 +268,40 @@ class PushReduceScatter(ReduceScatter):
             scale = 1.0
         else:
             raise _lib.TouchNetB200Error(f"PushReduceScatter: unsupported reduce op {op}")
-        recv = self._slot(n * pool.size)
+        stash, self._stash = self._stash, None
+        if stash is not None and stash[0] == input_tensor.data_ptr():
+            # ---- direct: chunk p of every gradient -> slot [rank] of peer p's receive buffer (own chunk: a local copy) ----
+            grads = stash[1]
+            dt = grads[0].dtype
+            recv = self._slot(n * pool.size, dt)
+            cur = torch.cuda.current_stream() if grads[0].is_cuda else None
+            off = 0
+            for g in grads:
+                flat = g.reshape(-1)
+                c = flat.numel() // pool.size
+                for k in range(pool.size):
+                    p = (pool.rank + k) % pool.size
+                    recv[p].view(pool.size, n)[pool.rank, off:off + c].copy_(flat[p * c:(p + 1) * c], non_blocking=True)
+                if cur is not None:
+                    g.record_stream(cur)         # allocated on the compute stream, read by copies on this (reduce-scatter) stream
+                off += c
+            if off != n:
+                raise _lib.TouchNetB200Error("direct reduce-scatter: gradient chunks do not add up to the shard size")
+            _barrier(pool.mem, 1)
+            mine = recv[pool.rank]
+            es = mine.element_size()
+            ptrs = [mine.data_ptr() + q * n * es for q in range(pool.size)]
+            if output_tensor.dtype != torch.float32:
+                raise _lib.TouchNetB200Error("PushReduceScatter produces fp32 (reduce_dtype=float32, the reference's default)")
+            if dt == torch.bfloat16:
+                _launch_reduce_bf16(ptrs, output_tensor, n, scale, self.max_ctas)
+            else:
+                _launch_reduce_scatter(ptrs, 0, output_tensor, n, scale, self.max_ctas)
+            return None
+        # ---- staged: FSDP2's copy-in filled `input_tensor` ([world, shard], reduce dtype) ----
+        if input_tensor.dtype != torch.float32:
+            raise _lib.TouchNetB200Error("PushReduceScatter handles fp32 reduce buffers (reduce_dtype=float32, the reference's default)")
+        recv = self._slot(n * pool.size, torch.float32)
         flat = input_tensor.reshape(-1)
         for k in range(1, pool.size):
             p = (pool.rank + k) % pool.size
@@ -220,14 +315,14 @@ class PushReduceScatter(ReduceScatter):
 
 
 def install(model: torch.nn.Module, group: dist.ProcessGroup, device, mem=None, all_gather: bool = True,
-            reduce_scatter: bool = True, max_ctas: int = 32, mode: str = "pull") -> _PeerPool:
+            reduce_scatter: bool = True, max_ctas: int = 32, mode: str = "pull", direct: bool = True) -> _PeerPool:
     """Give every FSDP2 module group of `model` the peer-memory collectives (call after `fully_shard`).
     mode "pull": tn_peer_* kernels read the peers' buffers; mode "push": copy-engine pushes + a local reduce kernel."""
     from torch.distributed.fsdp import FSDPModule
     if mode not in ("pull", "push"):
         raise ValueError(f"fsdp_comm.install: unknown mode {mode!r}")
     pool = _PeerPool(group, device, mem)
-    rs = (PeerReduceScatter if mode == "pull" else PushReduceScatter)(pool, max_ctas)
+    rs = PeerReduceScatter(pool, max_ctas) if mode == "pull" else PushReduceScatter(pool, max_ctas, direct=direct)
     ag = PeerAllGather(pool, max_ctas) if mode == "pull" else PushAllGather(pool)
     for m in model.modules():
         if isinstance(m, FSDPModule):

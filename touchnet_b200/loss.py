@@ -104,6 +104,85 @@ class LazyLogits:
         return f"LazyLogits(shape={tuple(self.shape)}, fused lm_head + loss; .materialize() for the tensor)"
 
 
+class VocabParallelLogits:
+    """`pred.logits` of a tensor-parallel model running loss parallel: this rank's vocabulary columns [v0, v0 + V/tp) of the
+    logits ([B, T, V/tp] bf16, part of the autograd graph) + the tp group.  Not a tensor; `materialize()` all-gathers."""
+
+    def __init__(self, local: torch.Tensor, group, v0: int, v_total: int):
+        self.local, self.group, self.v0, self.v_total = local, group, int(v0), int(v_total)
+        self.shape = torch.Size((*local.shape[:-1], v_total))
+        self.dtype, self.device = local.dtype, local.device
+        self._stats = None
+
+    def materialize(self) -> torch.Tensor:
+        import torch.distributed as dist
+        n = dist.get_world_size(self.group)
+        parts = [torch.empty_like(self.local) for _ in range(n)]
+        dist.all_gather(parts, self.local.detach().contiguous(), group=self.group)
+        return torch.cat(parts, dim=-1)
+
+    def dim(self) -> int:
+        return len(self.shape)
+
+
+class _VocabParallelCEFn(torch.autograd.Function):
+    """Pack-loss cross-entropy on vocabulary-sharded logits.  Per shard: tn_pack_ce_fwd_bf16 (local logsumexp, local label
+    term, local argmax); across the tp group: three [M]-sized all-reduces (max of the local logsumexps, sum of the rescaled
+    exponentials, the label logit from its owner); backward: tn_pack_ce_bwd_vp_bf16 in place on the local columns."""
+
+    @staticmethod
+    def forward(ctx, local, labels, sentence_lens, inv_num_sentence, group, v0, v_total):
+        import torch.distributed as dist
+        _check_logits(local)
+        Vl = local.shape[-1]
+        x = local.view(-1, Vl)
+        assert x.stride(1) == 1
+        M = x.shape[0]
+        lab = labels.reshape(-1).contiguous()
+        sl = sentence_lens.reshape(-1).contiguous()
+        lab_l = lab - v0                                                  # out of [0, Vl): "ignored" by the local kernel
+        lse_l = torch.empty(M, dtype=torch.float32, device=x.device)
+        ce_l = torch.empty(M, dtype=torch.float32, device=x.device)
+        am_l = torch.empty(M, dtype=torch.int32, device=x.device)
+        _lib.call("tn_pack_ce_fwd_bf16", x.data_ptr(), x.stride(0), lab_l.data_ptr(), lse_l.data_ptr(), ce_l.data_ptr(),
+                  am_l.data_ptr(), M, Vl, _st())
+        mine = (lab_l >= 0) & (lab_l < Vl)
+        m = lse_l.clone()
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+        ssum = torch.exp(lse_l - m)
+        dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=group)
+        lse = m + torch.log(ssum)
+        xlab = torch.where(mine, lse_l - ce_l, torch.zeros_like(lse_l))      # the label's logit, from the rank that owns it
+        dist.all_reduce(xlab, op=dist.ReduceOp.SUM, group=group)
+        valid = (lab >= 0) & (lab < v_total)
+        ce = torch.where(valid, lse - xlab, torch.zeros_like(lse))
+        # global argmax: best local value of every rank, lowest vocabulary index wins ties (torch.argmax semantics)
+        best = x.gather(1, am_l.long()[:, None]).squeeze(1).float()
+        n = dist.get_world_size(group)
+        vals = [torch.empty_like(best) for _ in range(n)]
+        idxs = [torch.empty_like(am_l) for _ in range(n)]
+        dist.all_gather(vals, best, group=group)
+        dist.all_gather(idxs, am_l + v0, group=group)
+        vals, idxs = torch.stack(vals), torch.stack(idxs)
+        win = vals.argmax(0)                                               # first (lowest-rank = lowest-index) maximum
+        am = idxs.gather(0, win[None]).squeeze(0)
+        ctx.save_for_backward(lab, sl, lse)
+        ctx.logits, ctx.inv_ns, ctx.shape, ctx.v0, ctx.v_total = x, inv_num_sentence, local.shape, v0, v_total
+        ctx.mark_non_differentiable(ce, am)
+        return (ce / sl.float()).sum() * inv_num_sentence, ce, am
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_ce, _g_am):
+        lab, sl, lse = ctx.saved_tensors
+        x = ctx.logits
+        g = g_loss.reshape(1).float().contiguous()
+        _lib.call("tn_pack_ce_bwd_vp_bf16", x.data_ptr(), x.stride(0), lab.data_ptr(), sl.data_ptr(), lse.data_ptr(),
+                  g.data_ptr(), float(ctx.inv_ns), x.shape[0], x.shape[1], ctx.v0, ctx.v_total, _st())
+        torch.autograd.graph.increment_version(x)
+        ctx.logits = None
+        return x.view(ctx.shape), None, None, None, None, None, None
+
+
 class FusedLinearCEFn(torch.autograd.Function):
     """loss_per_sample(h, W) of ref: touchnet/loss/cross_entropy.py:12-50 with logits = h . W^T never materialised.
     Gradients for an upstream gradient of 1 are produced during forward, chunk by chunk; backward scales them."""
@@ -183,6 +262,10 @@ def cross_entropy_loss(pred, labels: torch.Tensor, sentence_lens: torch.Tensor, 
         loss_per_sample, ce, am = fused_linear_cross_entropy(pred.hidden, pred.weight, labels, sentence_lens,
                                                              1.0 / max(int(num_sentence), 1))
         pred._stats = (ce, am)
+    elif isinstance(pred, VocabParallelLogits):
+        loss_per_sample, ce, am = _VocabParallelCEFn.apply(pred.local, labels, sentence_lens,
+                                                           1.0 / max(int(num_sentence), 1), pred.group, pred.v0, pred.v_total)
+        pred._stats = (ce, am)
     else:
         loss_per_sample, ce, am = _PackCEFn.apply(pred, labels, sentence_lens, 1.0 / max(int(num_sentence), 1))
         _LAST_ARGMAX = (weakref.ref(pred), pred._version, am)
@@ -196,6 +279,18 @@ def cross_entropy_loss(pred, labels: torch.Tensor, sentence_lens: torch.Tensor, 
 def accuracy(pred: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
     """Same contract as ref: touchnet/utils/metrics.py:26-50; reuses the argmax the loss kernel already produced."""
     V = pred.shape[-1]
+    if isinstance(pred, VocabParallelLogits):
+        if pred._stats is None:
+            with torch.no_grad():
+                ones = torch.ones(labels.numel(), dtype=torch.int64, device=labels.device)
+                _, ce, am = _VocabParallelCEFn.apply(pred.local.detach(), labels, ones, 1.0, pred.group, pred.v0, pred.v_total)
+            pred._stats = (ce, am)
+        am = pred._stats[1]
+        lab = labels.reshape(-1)
+        mask = lab != ignore_index
+        num = ((am.long() == lab) & mask).sum()
+        den = mask.sum()
+        return torch.where(den > 0, num / den.clamp(min=1), torch.zeros_like(num, dtype=torch.float32)).detach()
     if isinstance(pred, LazyLogits):
         if pred._stats is None:        # accuracy asked before / without the loss: one statistics-only fused pass
             with torch.no_grad():

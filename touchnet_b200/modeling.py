@@ -282,6 +282,10 @@ class B200LlamaForCausalLM(nn.Module):
     # loss.cross_entropy_loss / loss.accuracy consume without ever materialising [B,T,V].  The "*_b200" TrainSpecs switch it
     # on (train_spec.register: their loss_fn / acc_fn are exactly those two functions); direct users get real logits.
     fused_linear_ce = False
+    # tensor parallel only: keep the logits sharded on the vocabulary and let loss.cross_entropy_loss reduce per-row statistics
+    # over the tp group (the reference's `loss_parallel`, touchnet/utils/distributed.py:322-323); set by parallelize.py from
+    # parallel_dims.loss_parallel_enabled
+    loss_parallel = False
 
     def __init__(self, config):
         super().__init__()
@@ -372,9 +376,14 @@ class B200LlamaForCausalLM(nn.Module):
                 logits = _loss.LazyLogits(h, self.lm_head.weight)
             else:
                 logits = ops.linear(h, self.lm_head.weight)
-        else:       # h is the sequence shard; logits come back replicated [B, T, V]
+        else:       # h is the sequence shard
             from . import tensor_parallel
-            logits = tensor_parallel.lm_head(h, self.lm_head.weight, tensor_parallel.TPContext(tp_group, h.shape[0]))
+            tpc = tensor_parallel.TPContext(tp_group, h.shape[0])
+            if getattr(self, "loss_parallel", False) and self.training and torch.is_grad_enabled():
+                # logits stay sharded on the vocabulary; the spec's loss_fn / acc_fn reduce per-row statistics over tp
+                logits = tensor_parallel.lm_head_loss_parallel(h, self.lm_head.weight, tpc)
+            else:   # replicated [B, T, V] logits
+                logits = tensor_parallel.lm_head(h, self.lm_head.weight, tpc)
         out = CausalLMOutputWithPast(logits=logits)
         return out
 

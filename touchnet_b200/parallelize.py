@@ -76,6 +76,9 @@ def make_parallelize_fn(base_fn: Optional[Callable] = None) -> Callable:
             raise NotImplementedError("pipeline parallelism is outside the B200 hot path (SURVEY 8, out of scope)")
         if getattr(parallel_dims, "tp_enabled", False):
             tensor_parallel.apply_tp(model, world_mesh["tp"])
+            if getattr(parallel_dims, "loss_parallel_enabled", False):       # ref: parallelize_llama.py:127-131
+                lm = model.language_model if hasattr(model, "language_model") else model
+                lm.loss_parallel = True
         if getattr(parallel_dims, "cp_enabled", False):
             context_parallel.enable_context_parallel(model, world_mesh["cp"].get_group(), load_balance=_torch_cp_load_balance())
         if base_fn is not None:

@@ -197,6 +197,19 @@ def lm_head(h_s: torch.Tensor, weight: torch.Tensor, tp: TPContext) -> torch.Ten
     return _VocabGather.apply(logits_l, tp).view(B, Tl * tp.size, -1)
 
 
+def lm_head_loss_parallel(h_s: torch.Tensor, weight: torch.Tensor, tp: TPContext):
+    """Loss-parallel form (ref: touchnet/models/llama/parallelize_llama.py:127-131 `lm_head` output Shard(-1) +
+    touchnet/utils/distributed.py:322-323 `loss_parallel()`): the logits stay sharded on the vocabulary - this rank's
+    [B, T, V/tp] columns - inside a handle that loss.cross_entropy_loss / loss.accuracy consume; only per-row statistics
+    (logsumexp pieces, label logit, best value) cross the tp group instead of the [B*T, V] tensor."""
+    from . import loss as _loss
+    B, Tl, d = h_s.shape
+    h = _SeqGather.apply(h_s.reshape(B * Tl, d), tp)
+    logits_l = ops.linear(h, local(weight))
+    vl = logits_l.shape[-1]
+    return _loss.VocabParallelLogits(logits_l.view(B, Tl * tp.size, vl), tp.group, tp.rank * vl, vl * tp.size)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # sharding the parameters (what `parallelize_module` does in the reference)
 # ---------------------------------------------------------------------------------------------------------------

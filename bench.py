@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--cp", type=int, default=1, help="context-parallel degree (BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--with-optimizer", action="store_true",
+                    help="also time fwd + bwd + grad-norm clip + B200AdamW step (extras.with_optimizer; N=1): the optimizer "
+                         "kernel writes the bf16 working copies, so this loop has no fp32->bf16 cast kernels")
     ap.add_argument("--no-incumbent", action="store_true",
                     help="skip extras.incumbent (compiled flex_attention / cuBLAS / Liger / HF layer timed next to ours, N=1)")
     args = ap.parse_args()
@@ -121,6 +124,12 @@ def make_host_batch(seed: int, B: int, T: int, vocab: int):
         if ids.numel():
             meta["doc_lens"] += torch.bincount(ids)[1:].tolist()
     meta["nonpad_tokens"] = int((doc > 0).sum())
+    # compact form for the end-to-end arm: int16 PCM as stored on disk (touchnet/bin/make_data.py:202) +
+    # per-document tables; the five [B,T] integer buffers are then built ON the device (batching.assemble_on_device)
+    plan = batching.plan_documents(batching.synthetic_utterances(seed, vocab, stride=STRIDE, max_s=30.0), B, T, True)
+    wav16 = (wav * 32768.0).round().clamp(-32768, 32767).to(torch.int16).contiguous().pin_memory()
+    meta["plan"] = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in plan.items()}
+    meta["wav_i16"] = wav16
     return host, meta
 
 
@@ -135,6 +144,20 @@ def to_device(host: dict, dev) -> dict:
 
 def h2d_bytes(host: dict) -> int:
     return int(sum(v.numel() * v.element_size() for v in host.values()))
+
+
+def e2e_inputs(meta: dict, dev) -> dict:
+    """The end-to-end arm's per-step inputs: H2D of the int16 waveforms and the per-document tables, then the [B,T] integer
+    buffers assembled by tn_pack_layout_i64 on the device (bit-identical to the host batchers, tests/test_gpu_layout.py)."""
+    from touchnet_b200 import batching
+    d = batching.assemble_on_device(meta["plan"], dev)
+    d["wav"] = meta["wav_i16"].to(dev, non_blocking=True)
+    return d
+
+
+def e2e_h2d_bytes(meta: dict) -> int:
+    n = meta["wav_i16"].numel() * 2
+    return int(n + sum(v.numel() * v.element_size() for v in meta["plan"].values() if torch.is_tensor(v)))
 
 
 def run_step(model, d: dict, meta: dict, B: int, T: int, cp_slice=None):
@@ -643,21 +666,54 @@ def main():
     # ---------------- end-to-end arm: pinned host inputs, H2D inside, loss read back every step ----------------
     e2e = None
     if not args.no_e2e:
+        compact = os.environ.get("TN_E2E_COMPACT", "1") != "0" and cp == 1
+        feed = (lambda: e2e_inputs(meta, dev)) if compact else (lambda: to_device(host, dev))
         for _ in range(2):
-            float(one_step(to_device(host, dev)).item())
+            float(one_step(feed()).item())
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(args.steps):
-            l = one_step(to_device(host, dev))
+            l = one_step(feed())
             _ = float(l.item())                                  # D2H of the step's result
         t1.record()
         barrier()
         ms2 = t0.elapsed_time(t1)
         ms2 = dist_util.max_over_ranks(ms2, dev)
         e2e = {"value": tokens_per_step * args.steps / (ms2 * 1e-3), "unit": "tokens/s",
-               "h2d_bytes_per_step": h2d_bytes(host), "d2h_bytes_per_step": 4}
+               "h2d_bytes_per_step": e2e_h2d_bytes(meta) if compact else h2d_bytes(host), "d2h_bytes_per_step": 4,
+               "inputs": ("pinned host int16 waveforms + per-document tables; [B,T] id / label / position / mask buffers built "
+                          "on the device (tn_pack_layout_i64), fbank from int16") if compact else
+                         "pinned host fp32 waveforms + five host-built [B,T] int64 buffers"}
 
+    with_opt = None
+    if args.with_optimizer and world == 1:
+        # fwd + bwd + clip + AdamW (touchnet/utils/optimizer.py:127-172, distributed.py:426-491 equivalents, csrc/optim.cu):
+        # the clip coefficient is applied inside the AdamW kernel, which also writes next step's bf16 weights
+        from touchnet_b200 import optim as tn_optim
+        opt = tn_optim.B200AdamW(model.parameters(), lr=1e-5, betas=(0.9, 0.95), weight_decay=0.1)
+
+        def opt_step():
+            model.zero_grad(set_to_none=True)
+            l = run_step(model, resident, meta, B, T, cp_slice)      # no cache invalidation: the optimizer refreshed the copies
+            tn_optim.clip_grad_norm_(model.parameters(), 1.0, defer_to=opt)
+            opt.step()
+            return l
+        for _ in range(3):
+            opt_step()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(args.steps):
+            opt_step()
+        o1.record()
+        barrier()
+        ms3 = o0.elapsed_time(o1)
+        with_opt = {"value": tokens_per_step * args.steps / (ms3 * 1e-3), "unit": "tokens/s", "ms_per_step": ms3 / args.steps,
+                    "what": "fwd + bwd + fused grad-norm clip + B200AdamW step, fp32 master weights and moments; no "
+                            "fp32->bf16 cast kernels in the loop (the AdamW kernel writes the bf16 working copies)",
+                    "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        del opt
     if os.environ.get("TN_TRACE"):            # diagnostic: device timeline of ONE more step (not part of any number)
         trace_one_step(lambda: one_step(resident), os.environ["TN_TRACE"], rank, barrier)
 
@@ -692,7 +748,7 @@ def main():
                                       "their own shard layout)"},
                    "model_tflop_per_step_rank0": gemm_flops / args.steps / 1e12,
                    "ms_by_entry_point_timed_region": gt.by_class(),
-                   "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                   "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "with_optimizer": with_opt,
                    "report_columns_rank0": derived_columns(gt.by_class(), args.steps, ms / args.steps, attn_fwd,
                                                            meta["nonpad_tokens"], B * T, B, T, n_layers, peaks, _W["text"],
                                                            attn_tile_flops_fwd_per_layer(host["attention_mask"],

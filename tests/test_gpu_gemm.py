@@ -137,7 +137,11 @@ def test_gemm_dswiglu_equals_dgrad_then_swiglu_backward(M, N, K):
     g = torch.randn(M, N, device=dev).bfloat16()
     u = torch.randn(M, N, device=dev).bfloat16()
     dg_ref, du_ref = ops.swiglu_bwd(g, u, ops.gemm(dy, wd, b_mn=True))
-    dg, du = ops.gemm_dswiglu(dy, wd, g, u)
+    ops._FUSE_DSWIGLU, saved = True, ops._FUSE_DSWIGLU            # the fused launch is opt-in (TN_FUSED_DSWIGLU=1)
+    try:
+        dg, du = ops.gemm_dswiglu(dy, wd, g, u)
+    finally:
+        ops._FUSE_DSWIGLU = saved
     assert torch.equal(dg, dg_ref) and torch.equal(du, du_ref)
     # and against fp32 math: dG = dH * u * silu'(g), dU = dH * silu(g)
     dh = dy.float() @ wd.float()

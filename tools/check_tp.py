@@ -59,4 +59,35 @@ if rank == 0:
     print(f"TP{world}{' audio' if audio else ''}: max |logits - unsharded| = {res[0].item():.4g} (scale {scale:.3g}); worst grad rel err = {res[1].item():.4g}")
     assert res[0].item() < 3e-2 * scale and res[1].item() < 3e-2
     print("TP OK")
+# ---- loss parallel (ref: parallelize_llama.py:127-131 + distributed.py:322-323): vocabulary-sharded logits into the pack-loss ----
+if os.environ.get("TP_LOSS_PARALLEL", "1") != "0":
+    from touchnet_b200 import loss as tn_loss
+    labels = torch.randint(0, text.vocab_size, (B, T), generator=g).to(dev)
+    labels[doc == 0] = -100
+    sl = torch.randint(1, 30, (B, T), generator=g).to(dev)
+    ref_model.zero_grad(); model.zero_grad()
+    lps_ref, lpt_ref = tn_loss.cross_entropy_loss(ref_model(**kw).logits, labels, sl, 7)
+    acc_ref = tn_loss.accuracy(ref_model(**kw).logits, labels)
+    lps_ref.backward()
+    ref_grads = {n: p.grad.detach().clone() for n, p in ref_model.named_parameters()}
+    lm = model.language_model if hasattr(model, "language_model") else model
+    lm.loss_parallel = True
+    model.train()
+    pred = model(**kw).logits
+    assert isinstance(pred, tn_loss.VocabParallelLogits) and pred.local.shape[-1] == text.vocab_size // world
+    lps, lpt = tn_loss.cross_entropy_loss(pred, labels, sl, 7)
+    acc = tn_loss.accuracy(pred, labels)
+    lps.backward()
+    worst = 0.0
+    for n, p in model.named_parameters():
+        gfull = p.grad.full_tensor() if tensor_parallel.is_dtensor(p.grad) else p.grad
+        worst = max(worst, rel_err(gfull.float(), ref_grads[n].float()))
+    res = torch.tensor([abs(float(lps) - float(lps_ref)) / abs(float(lps_ref)), abs(float(lpt) - float(lpt_ref)) / abs(float(lpt_ref)),
+                        abs(float(acc) - float(acc_ref)), worst], device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"TP{world} loss parallel: rel loss err {res[0].item():.3g} / {res[1].item():.3g}, |acc diff| {res[2].item():.3g}, "
+              f"worst grad rel err {res[3].item():.4g}")
+        assert res[0].item() < 2e-3 and res[1].item() < 2e-3 and res[2].item() < 2e-3 and res[3].item() < 3e-2
+        print("TP LOSS PARALLEL OK")
 dist.destroy_process_group()

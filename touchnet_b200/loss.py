@@ -75,8 +75,10 @@ class _PackCEFn(torch.autograd.Function):
         return x.view(ctx.shape), None, None, None
 
 
-FUSED_CE_CHUNK = 2048     # token rows per chunk: the [chunk, V] buffer is 0.5 GB at V = 128 k instead of 2.1 GB for T = 8192,
-                          # and a 2048-row wgrad GEMM (1.5 ms) still hides the read-modify-write of the fp32 dW (0.65 ms)
+FUSED_CE_CHUNK = 4096     # token rows per chunk: the [chunk, V] buffer is 1 GB at V = 128 k instead of 2.1 GB for T = 8192.  Measured
+                          # (profiles/r02_bench_n1_dswiglu_fused.json by_shape): with 2048-row chunks the accumulating fp32 wgrad
+                          # (K = 2048, read-modify-write of the 2.1 GB dW per chunk) runs at 953 TFLOP/s, 2.4 ms per step slower
+                          # than with K >= 4096
 
 
 class LazyLogits:

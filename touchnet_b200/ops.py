@@ -237,7 +237,11 @@ def gemm_qkv_wgrad(dqkv, x, f32: bool, nq: int | None = None, nkv: int | None = 
     return outs
 
 
-_FUSE_DSWIGLU = os.environ.get("TN_FUSED_DSWIGLU", "1") != "0"   # A/B switch for measurements
+# Measured in the 32-layer step (profiles/r02_bench_n1_dswiglu_fused.json): the fused launch runs at 828 TFLOP/s (its epilogue
+# - strided G/U loads, 2 exp per element, two stores - outlasts the K=4096 mainloop it should hide behind) against 1400 for the
+# plain dgrad + a 0.22 ms SwiGLU-backward pass, i.e. 0.25 ms per layer SLOWER.  Kept (bit-identical, tested) behind
+# TN_FUSED_DSWIGLU=1; the default is the two-kernel path until the epilogue reads G/U through TMA.
+_FUSE_DSWIGLU = os.environ.get("TN_FUSED_DSWIGLU", "0") != "0"
 
 
 def gemm_dswiglu(dy: torch.Tensor, wd: torch.Tensor, g: torch.Tensor, u: torch.Tensor):

@@ -29,7 +29,8 @@ def small_cfg(L=2, d=256, H=2, KV=1, ffn=512, V=512, rope_scaling=None, bias=Fal
 def oracle_cfg(c, audio=0):
     return mo.OracleConfig(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
                            num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
-                           num_key_value_heads=c.num_key_value_heads, head_dim=128, vocab_size=c.vocab_size,
+                           num_key_value_heads=c.num_key_value_heads, head_dim=getattr(c, "head_dim", 128),
+                           vocab_size=c.vocab_size,
                            rms_norm_eps=c.rms_norm_eps, rope_theta=c.rope_theta, rope_scaling=c.rope_scaling,
                            attention_bias=c.attention_bias, audio_input_size=audio,
                            pad_token_id=getattr(c, "pad_token_id", None))
@@ -141,6 +142,35 @@ def test_touch_audio_forward_backward_parity():
         model.raise_if_nan()
     feats[0, 3, 5] = 0.0
     model(input_ids=ids, input_features=feats, attention_mask=doc, position_ids=pos)    # the flag was cleared
+
+
+@pytest.mark.parametrize("hd,H,KV", [(64, 4, 2), (32, 8, 8)])
+def test_head_dim_below_128_runs_through_zero_padded_heads(hd, H, KV):
+    """The reference's example config is head_dim 64 (examples/text/pretrain/fineweb-edu/config/Llama-3_2-1B.json:13): such
+    models run through the 128-wide attention kernels with zero-padded heads (exact: zero q/k columns add nothing to the
+    scores, zero v columns give zero outputs).  Forward logits and every parameter gradient vs the oracle."""
+    dev = require_cuda()
+    cfg = small_cfg(L=2, d=256, H=H, KV=KV, ffn=512, V=512, rope_scaling=LLAMA3)
+    cfg.head_dim = hd
+    B, T = 2, 384
+    torch.manual_seed(2025)
+    model = modeling.B200LlamaForCausalLM(cfg).to(dev)
+    model.post_init()
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 2:
+                p.normal_(0, 0.05)
+    doc, pos = packed_doc_ids(B, T, [[100, 200, 50], [384]], dev)
+    ids = torch.randint(1, cfg.vocab_size, (B, T), device=dev)
+    logits = model(input_ids=ids, attention_mask=doc, position_ids=pos).logits
+    (logits.float()[doc > 0]).square().mean().backward()
+    params32 = {k: v.detach().bfloat16().float().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = mo.llama_forward(params32, oracle_cfg(cfg), input_ids=ids, attention_mask=doc, position_ids=pos, dtype=torch.float32)
+    _check_logits(logits, ref, doc > 0)
+    ref[doc > 0].square().mean().backward()
+    for name, p in model.named_parameters():
+        e = rel_err(p.grad.float(), params32[name].grad)
+        assert e < 3e-2, (name, e)
 
 
 @pytest.mark.parametrize("mode", ["full", "selective_op"])

@@ -84,11 +84,18 @@ def test_rope_parameters_match_golden_inv_freq(golden_dir):
     assert torch.equal(inv, torch.from_numpy(g["llama/inv_freq"]))   # HF llama3 rope init, bit exact
 
 
-def test_head_dim_other_than_128_is_refused_loudly():
+def test_head_dim_other_than_128_is_padded_or_refused_loudly():
+    """head_dim 64 (the reference's example config Llama-3_2-1B.json:13) is accepted - it runs through the 128-wide attention
+    kernels with zero-padded heads (tests/test_gpu_model.py) - anything the kernels cannot express is refused at construction."""
     c = _cfg()
     c.head_dim = 64
-    with pytest.raises(Exception, match="head_dim 128"):
-        modeling.B200LlamaForCausalLM(c)
+    m = modeling.B200LlamaForCausalLM(c)
+    a = m.model.layers[0].self_attn
+    assert a.head_dim == 64 and a.q_proj.weight.shape[0] == a.num_heads * 64
+    for bad in (256, 60):
+        c.head_dim = bad
+        with pytest.raises(Exception, match="head_dim 128"):
+            modeling.B200LlamaForCausalLM(c)
 
 
 def test_cpu_tensors_are_refused_loudly():

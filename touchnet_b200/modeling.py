@@ -158,7 +158,7 @@ class B200DecoderLayer(nn.Module):
                 hidden_states, self.input_layernorm.weight, a.q_proj.weight, a.k_proj.weight, a.v_proj.weight,
                 a.q_proj.bias, a.k_proj.bias, a.v_proj.bias, a.o_proj.weight, self.post_attention_layernorm.weight,
                 m.gate_proj.weight, m.up_proj.weight, m.down_proj.weight, cos, sin, plan, a.num_heads,
-                a.num_key_value_heads, self.input_layernorm.variance_epsilon)
+                a.num_key_value_heads, self.input_layernorm.variance_epsilon, a.head_dim)
         # tensor parallel (tensor_parallel.py): this rank's weight shards, H/tp and KV/tp heads
         from .tensor_parallel import local
         wq, wk = local(a.q_proj.weight), local(a.k_proj.weight)
@@ -183,8 +183,9 @@ class B200LlamaModel(nn.Module):
         self.norm = B200RMSNorm(config.hidden_size, _cfg(config, "rms_norm_eps", 1e-6))
         self.rotary_emb = B200RotaryEmbedding(config)
         hd = _cfg(config, "head_dim", config.hidden_size // config.num_attention_heads)
-        if hd != 128:
-            raise TouchNetB200Error(f"touchnet_b200 attention kernels are built for head_dim 128, config has {hd}")
+        if hd > 128 or hd % 8:
+            raise TouchNetB200Error(f"touchnet_b200 attention kernels are built for head_dim 128 (smaller multiples of 8 run "
+                                    f"through them with zero-padded heads); config has {hd}")
 
     def forward(self, inputs_embeds: torch.Tensor, attention_mask: Optional[torch.Tensor],
                 position_ids: Optional[torch.Tensor]):

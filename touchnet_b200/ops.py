@@ -530,6 +530,18 @@ def swiglu_mlp_in(x, wg, wu):
     return SwiGLUFn.apply(x, wg, wu, bf16_weight(wg), bf16_weight(wu))
 
 
+def _pad_heads(x: torch.Tensor, heads: int, hd: int) -> torch.Tensor:
+    """[rows, heads*hd] -> [rows, heads*128] with every head zero-padded to the 128 columns the attention kernels are built
+    for: zero q/k columns add nothing to the scores, zero v columns give zero output columns - the result is exact."""
+    out = torch.zeros((x.shape[0], heads, 128), dtype=x.dtype, device=x.device)
+    out[:, :, :hd] = x.reshape(x.shape[0], heads, hd)
+    return out.view(x.shape[0], heads * 128)
+
+
+def _unpad_heads(x: torch.Tensor, heads: int, hd: int) -> torch.Tensor:
+    return x.view(x.shape[0], heads, 128)[:, :, :hd].reshape(x.shape[0], heads * hd)
+
+
 class DecoderLayerFn(torch.autograd.Function):
     """One pre-norm decoder block as a single autograd node (hf: LlamaDecoderLayer.forward modeling_llama.py:303-333):
     7 kernel launches forward, residual adds fused into the o_proj / down_proj GEMM epilogues, q/k/v projections one
@@ -540,9 +552,11 @@ class DecoderLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ln1, wq, wk, wv, bq, bk, bv, wo, ln2, wg, wu, wd, wqb, wkb, wvb, wob, wgb, wub, wdb, cos, sin,
-                plan, H, KV, eps):
+                plan, H, KV, eps, hd=128):
         x2 = _rows2d(x)
-        scale = 1.0 / math.sqrt(128)
+        scale = 1.0 / math.sqrt(hd)
+        if hd != 128 and (hd > 128 or hd % 8 or plan.tp is not None or plan.cp_group is not None):
+            raise _lib.TouchNetB200Error(f"head_dim {hd}: only multiples of 8 up to 128, without tensor / context parallelism")
         tp = plan.tp                # tensor + sequence parallel: x holds T/tp rows, weights are this rank's shards
         if tp is not None and plan.cp_group is not None:
             raise _lib.TouchNetB200Error("tensor parallelism and context parallelism cannot be combined in one block")
@@ -550,7 +564,7 @@ class DecoderLayerFn(torch.autograd.Function):
         if tp is not None:
             h1 = tp.gather_rows(h1, keep=True)                               # [B*T, d]: every row, for the local heads
         nq, nkv = wq.shape[0], wk.shape[0]
-        rope_in_gemm = qkv_fusable(h1.shape[0], nq, nkv) and bq is None     # RoPE in the QKV GEMM epilogue
+        rope_in_gemm = qkv_fusable(h1.shape[0], nq, nkv) and bq is None and hd == 128   # RoPE in the QKV GEMM epilogue
         if qkv_fusable(h1.shape[0], nq, nkv):
             qkv = gemm_qkv_fwd(h1, wqb, wkb, wvb, rope=(cos, sin) if rope_in_gemm else None)
             q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
@@ -559,15 +573,17 @@ class DecoderLayerFn(torch.autograd.Function):
         if bq is not None:
             q += bq.to(BF16); k += bk.to(BF16); v += bv.to(BF16)
         if not rope_in_gemm:
-            rope_apply_(q, cos, sin, H, 128)
-            rope_apply_(k, cos, sin, KV, 128)
+            rope_apply_(q, cos, sin, H, hd)
+            rope_apply_(k, cos, sin, KV, hd)
+        if hd != 128:      # head_dim 64 (Llama-3.2-1B, the reference's example config) etc.: zero-padded heads, 128-wide kernels
+            q, k, v = _pad_heads(q, H, hd), _pad_heads(k, KV, hd), _pad_heads(v, KV, hd)
         if plan.cp_group is None:
             o, lse = attn_fwd(q, k, v, plan, H, KV, scale)
         else:   # context parallel: K/V of all cp ranks are gathered, the kernel runs on this rank's query window
             from . import context_parallel as _cp
             o, lse, k, v = _cp.cp_attn_fwd(q, k, v, plan, H, KV, scale)
         if tp is None:
-            x1 = gemm(o, wob, residual=x2)
+            x1 = gemm(o if hd == 128 else _unpad_heads(o, H, hd), wob, residual=x2)
         else:                                                                # partial sums over tp -> this rank's rows
             x1 = tp.gemm_reduce_scatter(o, wob, x2)
         h2, _, rstd2 = rmsnorm_fwd(x1, ln2, eps)
@@ -580,7 +596,7 @@ class DecoderLayerFn(torch.autograd.Function):
             out = tp.gemm_reduce_scatter(hm, wdb, x1)
         ctx.save_for_backward(x2, ln1, ln2, wqb, wkb, wvb, wob, wgb, wub, wdb, cos, sin, rstd1, h1, q, k, v, o, lse, x1,
                               rstd2, h2, g, u, hm)
-        ctx.plan, ctx.H, ctx.KV, ctx.scale, ctx.has_bias = plan, H, KV, scale, bq is not None
+        ctx.plan, ctx.H, ctx.KV, ctx.scale, ctx.has_bias, ctx.hd = plan, H, KV, scale, bq is not None, hd
         ctx.f32 = wq.dtype == torch.float32
         ctx.w_dtype = wq.dtype
         return out.view(x.shape)
@@ -609,8 +625,11 @@ class DecoderLayerFn(torch.autograd.Function):
         dx1, dln2 = rmsnorm_bwd(x1, dh2, ln2, rstd2, ds_extra=d2)
         # ---- attention ----
         dx1f = dx1 if tp is None else tp.gather_rows(dx1)
+        hd = ctx.hd
         do = gemm(dx1f, wob, b_mn=True)
-        dwo = _wgrad(dx1f, o, f32)
+        dwo = _wgrad(dx1f, o if hd == 128 else _unpad_heads(o, H, hd), f32)
+        if hd != 128:
+            do = _pad_heads(do, H, hd)
         del dx1f
         nq, nkv = wqb.shape[0], wkb.shape[0]
         fused = qkv_fusable(h1.shape[0], nq, nkv)
@@ -622,6 +641,14 @@ class DecoderLayerFn(torch.autograd.Function):
                 dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
             rope_apply_(dq, cos, sin, H, 128, inverse=True)
             rope_apply_(dk, cos, sin, KV, 128, inverse=True)
+        elif hd != 128:   # padded heads: gradients of the padded tensors, un-padded, then the inverse rotation at head_dim hd
+            dqp, dkp, dvp = attn_bwd(q, k, v, o, do, lse, ctx.plan, H, KV, ctx.scale)
+            dq, dk, dv = _unpad_heads(dqp, H, hd), _unpad_heads(dkp, KV, hd), _unpad_heads(dvp, KV, hd)
+            rope_apply_(dq, cos, sin, H, hd, inverse=True)
+            rope_apply_(dk, cos, sin, KV, hd, inverse=True)
+            if fused:
+                dqkv = torch.cat([dq, dk, dv], dim=1)
+                dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
         elif fused:   # inverse RoPE happens in the attention-backward epilogues
             dqkv = torch.empty((h1.shape[0], nq + 2 * nkv), dtype=BF16, device=x2.device)
             dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
@@ -646,10 +673,10 @@ class DecoderLayerFn(torch.autograd.Function):
             tp.all_reduce_(dln1)
             tp.all_reduce_(dln2)
         return (dx.view(dout.shape), dln1.to(ln1.dtype), dwq, dwk, dwv, dbq, dbk, dbv, dwo, dln2.to(ln2.dtype), dwg, dwu,
-                dwd) + (None,) * 13
+                dwd) + (None,) * 14
 
 
-def decoder_layer(x, ln1, wq, wk, wv, bq, bk, bv, wo, ln2, wg, wu, wd, cos, sin, plan, H, KV, eps):
+def decoder_layer(x, ln1, wq, wk, wv, bq, bk, bv, wo, ln2, wg, wu, wd, cos, sin, plan, H, KV, eps, hd=128):
     return DecoderLayerFn.apply(x, ln1, wq, wk, wv, bq, bk, bv, wo, ln2, wg, wu, wd, bf16_weight(wq), bf16_weight(wk),
                                 bf16_weight(wv), bf16_weight(wo), bf16_weight(wg), bf16_weight(wu), bf16_weight(wd),
-                                cos, sin, plan, H, KV, eps)
+                                cos, sin, plan, H, KV, eps, hd)

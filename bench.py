@@ -369,13 +369,15 @@ def derived_columns(by_class: dict, steps: int, ms_per_step: float, attn_fwd_flo
 
 
 def gemm_traffic():
-    """Average DRAM bytes per GEMM launch of the step, from the committed ncu capture (profiles/r01_gemm_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
-            return None
+    """Average DRAM bytes per GEMM launch of the step, from the newest committed ncu capture (profiles/rNN_gemm_traffic.json,
+    produced by tools/gemm_traffic.py from an `ncu --metrics dram__bytes_*` run of this very command with --layers 2)."""
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            try:
+                return json.load(open(p))
+            except Exception:
+                continue
     return None
 
 

@@ -27,7 +27,9 @@ LAYER_BWD = [g(M, FFN, D),                                  # down dgrad
              g(FFN, D, M, out=F32), g(FFN, D, M, out=F32),  # gate / up wgrad
              g(M, NQ, D), g(D, NQ, M, out=F32),             # o dgrad, wgrad
              g(M, D, QKV), g(QKV, D, M, out=F32)]           # fused QKV dgrad, wgrad
-OUTSIDE = [g(M, D, F), g(D, F, M, out=F32), g(M, V, D), g(M, D, V), g(V, D, M, out=F32)]
+NCH, MC = 2, 4096                                              # fused lm_head + loss: chunks of 4096 token rows (loss.FUSED_CE_CHUNK)
+OUTSIDE = [g(M, D, F), g(D, F, M, out=F32)] + [
+    x for c in range(NCH) for x in (g(MC, V, D), g(MC, D, V), g(V, D, MC, out=F32, extra=(V * D * F32 if c else 0)))]
 L = 32
 ALG_TOTAL = L * (sum(LAYER_FWD) + sum(LAYER_BWD)) + sum(OUTSIDE)
 N_LAUNCH = L * (len(LAYER_FWD) + len(LAYER_BWD)) + len(OUTSIDE)
@@ -45,13 +47,15 @@ def main(path, out):
         d = per.setdefault(int(r[ii]), {})
         d[r[mi]] = float(r[vi].replace(",", ""))
     launches = [per[k] for k in sorted(per)]
-    per_step = 2 * 14 + 5
+    per_step = 2 * 14 + 2 + 3 * NCH
     assert len(launches) >= per_step and len(launches) % per_step == 0, (len(launches), per_step)
     last = launches[-per_step:]
     dram = [x["dram__bytes_read.sum"] + x["dram__bytes_write.sum"] for x in last]
-    # launch order inside a step: projector fwd | 2 x 4 block fwd | lm_head fwd, dgrad, wgrad | 2 x 10 block bwd | projector wgrad
-    block = sum(dram[1:9]) + sum(dram[12:32])
-    outside = dram[0] + sum(dram[9:12]) + dram[32]
+    # launch order inside a step: projector fwd | 2 x 4 block fwd | NCH x (lm_head fwd, dgrad, wgrad) | 2 x 10 block bwd |
+    # projector wgrad
+    h0 = 9 + 3 * NCH
+    block = sum(dram[1:9]) + sum(dram[h0:h0 + 20])
+    outside = dram[0] + sum(dram[9:h0]) + dram[h0 + 20]
     total = block * (L / 2) + outside
     res = {"source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:gemm on bench.py --layers 2 ({path}), "
                      "block launches scaled to 32 layers (tools/gemm_traffic.py)",

@@ -244,7 +244,7 @@ int tn_pack_layout_i64(const int32_t* doc_row, const int32_t* doc_off, const int
                        int64_t* sentence_lens, tn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Data-parallel collectives over NVLink peer memory (EXPERIMENTAL; SURVEY 8(e) "NCCL's or your own").  What FSDP2 does
+ * Data-parallel collectives over NVLink peer memory (SURVEY 8(e) "NCCL's or your own"; touchnet_b200/fsdp_comm.py).  What FSDP2 does
  * through NCCL around every decoder block (touchnet/models/helper_func.py:134-202: fp32 gradient reduce-scatter, bf16
  * parameter all-gather) as pull kernels on buffers every rank has mapped (torch symmetric memory):
  *   tn_peer_reduce_scatter_f32: out[i] = scale * sum_{p<n_peers} inputs[p][shard_offset + i], i < numel, summed in rank

@@ -106,7 +106,7 @@ def _reduce_scatter_seq(x: torch.Tensor, B: int, group, head_tail: bool = False)
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# halo exchange (EXPERIMENTAL, opt-in with TN_CP_HALO=1): move only the K/V rows a rank's queries can reach
+# halo exchange (default; TN_CP_HALO=0 = whole-shard all-gather): move only the K/V rows a rank's queries can reach
 # ---------------------------------------------------------------------------------------------------------------
 # With packed documents a query never looks past the start of its own document, so rank r needs K/V only from the first
 # block of the earliest document that reaches into its window (the per-block `kv_lo` the attention kernels already use)

@@ -1,4 +1,4 @@
-// touchnet_b200 :: data-parallel collectives over NVLink peer memory (EXPERIMENTAL groundwork).
+// touchnet_b200 :: data-parallel collectives over NVLink peer memory (driven by touchnet_b200/fsdp_comm.py).
 //
 // FSDP2 (ref: touchnet/models/helper_func.py:134-202) reduce-scatters the fp32 gradients of every decoder block and
 // all-gathers its bf16 parameters through NCCL.  With every rank's communication buffer mapped into every other rank's

@@ -1,24 +1,30 @@
-"""FSDP2 collectives over NVLink peer memory with our own kernels (EXPERIMENTAL groundwork, opt-in).
+"""FSDP2 collectives over NVLink symmetric memory (what bench.py runs at N > 1; NCCL stays the library default).
 
 FSDP2 (ref: touchnet/models/helper_func.py:134-202) lets a module group swap its communication primitives
 (`FSDPModule.set_custom_reduce_scatter / set_custom_all_gather`, torch/distributed/fsdp/_fully_shard/_fsdp_api.py).
-`PeerReduceScatter` / `PeerAllGather` allocate FSDP2's communication buffers in symmetric memory (every rank maps every
-rank's buffer, CUDA IPC over NVLink) and replace the NCCL ring kernels by one pull kernel each
-(csrc/collective.cu: tn_peer_reduce_scatter_f32 / tn_peer_all_gather) between two device-side barriers' worth of ordering:
+`install(model, group, device, mode=...)` gives every group buffers in torch symmetric memory (every rank maps every rank's
+buffer, CUDA IPC over NVLink / NVSwitch) and one of two forms:
 
-    reduce-scatter   barrier (every rank's gradient copy-in is complete)  ->  out = 1/N * sum_p in_p[my shard]
-    all-gather       barrier (every rank's shard copy-in is complete)     ->  out[p] = in_p[p's shard]  for all p
+  mode="push" (measured best, profiles/r02_bench_n{2,4,8}_*.json)
+    all-gather      every rank copies its shard into every peer's output buffer with plain device-to-device copies
+                    (copy engines, no SM), one device-side barrier                                      -> PushAllGather
+    reduce-scatter  direct: FSDP2's chunk_cat copy-in (a kernel on the COMPUTE stream) is bypassed; chunk p of every
+                    unsharded gradient (bf16 under the mixed-precision policy) is pushed from where autograd left it into
+                    peer p's receive slot, one barrier, then tn_reduce_bf16_to_f32 adds the N chunks in rank order in fp32
+                    (= fp32 reduce of the bf16 gradients, deterministic).  staged: FSDP2's [world, shard] fp32 input buffer
+                    is filled as usual and its chunks are pushed                                          -> PushReduceScatter
+  mode="pull"  (round 1's idea; measured SLOWER than NCCL: too few bytes in flight per CTA)
+    tn_peer_reduce_scatter_f32 / tn_peer_all_gather read the peers' buffers                 -> PeerReduceScatter / PeerAllGather
 
-Why: at N=2 the NCCL reduce-scatter (ring, LL protocol) is busy 79 ms of a 407 ms step and slows the backward GEMMs it
-overlaps by 17 %; a pull of 8 GB over NVLink is ~12 ms of a few CTAs.  Buffers come from a ring of three
-per size: a buffer is rewritten only after later barriers which every reader reaches after its pull (stream order; FSDP2
-itself orders the next copy-in behind the previous collective of the same kind).  To be confirmed on hardware: that
-ordering across FSDP2's copy-in / collective streams, and the SM budget (`max_ctas`).
+Why: NCCL's ring kernels share SMs / L2 / HBM with the backward GEMMs they overlap (+40 ms of a 408 ms step at N=2) and
+FSDP2's copy-in runs on the compute stream (+26 ms).  With pushes the tensor-core kernels keep the whole chip: 408 -> 364 ms
+per step at N=2, 425 -> 373 ms at N=8 (154 k -> 175 k tokens/s).
 
-STATUS: written at the end of round 1 after the GPU minutes were spent.  The Comm plumbing (allocate / call protocol,
-barrier placement, buffer ring) is verified on CPU with FSDP2 over gloo, shared-memory files standing in for symmetric
-memory and torch standing in for the two kernels (tests/test_parallel_gloo.py); it has NOT run on hardware.  Opt-in:
-`fsdp_comm.install(model, mesh)` after `fully_shard`, or TN_FSDP_PEER=1 for bench.py.
+Ordering: a buffer of the ring of three is rewritten only after later barriers which every reader reaches after it has
+consumed the buffer (stream order); all-gather and reduce-scatter barriers use different signal-pad channels because the
+two collectives overlap in backward.  Parity on hardware: tools/check_fsdp.py (TN_FSDP_PEER=1|push, TN_FSDP_DIRECT=0|1) on
+2 GPUs, the rank-0 loss of every bench line at N = 2, 4, 8; wiring on CPU: tests/test_parallel_gloo.py (gloo, shared-memory
+files standing in for symmetric memory, torch standing in for the kernels).
 """
 from __future__ import annotations
 

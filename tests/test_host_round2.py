@@ -94,6 +94,8 @@ def test_direct_push_eligibility_rule():
     assert not comm.can_direct([torch.zeros(16, 3, dtype=torch.bfloat16)], 4)       # 4 x 3 x 2 B chunks: not 16-byte multiples
     assert not comm.can_direct([torch.zeros(16, 32, dtype=torch.float16)], 4)
     assert not comm.can_direct([], 4)
+    comm.pool = type("P", (), {"size": 1, "rank": 0})()          # 1-rank group: FSDP2 never calls the reduce-scatter, so the
+    assert not comm.can_direct(ok, 1)                            # copy-in must not be skipped
 
 
 def _pair_work(w, num_tiles, C, allow=True):

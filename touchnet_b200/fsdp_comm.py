@@ -242,8 +242,8 @@ class PushReduceScatter(ReduceScatter):
         return t
 
     def can_direct(self, grads, world_size: int) -> bool:
-        if world_size != self.pool.size or not grads:
-            return False
+        if world_size != self.pool.size or world_size < 2 or not grads:
+            return False        # (a 1-rank group: FSDP2 copies the input buffer itself instead of calling the reduce-scatter)
         dt = grads[0].dtype
         if dt not in (torch.bfloat16, torch.float32):
             return False
